@@ -1,0 +1,200 @@
+/*
+ * include/slq.h -- C ABI of libslq_b200.so: the B200 (sm_100a) hot path of
+ * kenm-28/Semilayer-Wise-Mixed-Precision-Quantization.
+ *
+ * The reference has no FFI of its own (it is pure Python on torch).  Each entry point below cites
+ * the reference call site whose ATen kernels it replaces; INTEGRATION.md shows the ctypes binding a
+ * maintainer adds to functions.py / resnet.py.
+ *
+ * Conventions
+ *   - plain C types only: pointers + sizes, no torch types, no C++ exceptions across the boundary;
+ *   - the caller owns every buffer (the Python host allocates them with torch) -- the library
+ *     allocates device memory only inside the *_host convenience calls;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns SLQ_OK or an SLQ_ERR_* code; slq_last_error() gives the message;
+ *   - device entry points only enqueue work: they never synchronise;
+ *   - safe to call from one host thread per device.
+ */
+#ifndef SLQ_H_
+#define SLQ_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLQ_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SLQ_API __attribute__((visibility("default")))
+#else
+#define SLQ_API
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define SLQ_OK 0
+#define SLQ_ERR_INVALID 1     /* bad argument (message says which) */
+#define SLQ_ERR_CUDA 2        /* a CUDA runtime / driver call failed */
+#define SLQ_ERR_ZERO_RANGE 3  /* constant row: the reference raises ZeroDivisionError (functions.py:40) */
+#define SLQ_ERR_UNSUPPORTED 4 /* shape outside what the kernels implement */
+
+/* per-row status written by the quantizer kernels (bit flags) */
+#define SLQ_ROW_OK 0
+#define SLQ_ROW_ZERO_RANGE 1 /* max == min: scale == 0 (row left untouched) */
+#define SLQ_ROW_CODE_RANGE 2 /* a code fell outside [0, 2^bit-1] and was clamped */
+
+/* fp32 divide flavour of functions.py:41 `tensor/scale` */
+#define SLQ_DIV_TRUE 0  /* IEEE fp32 divide: what ATen does for CPU tensors */
+#define SLQ_DIV_RECIP 1 /* multiply by the fp32 reciprocal: ATen CUDA div by a CPU scalar */
+
+SLQ_API const char *slq_last_error(void);
+SLQ_API int slq_abi_version(void);
+/* sm_count / cc_major / cc_minor of the current device (any pointer may be NULL) */
+SLQ_API int slq_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* =============================================================================================
+ * 1. Per-channel affine quantizer
+ *    replaces  functions.py:25-43  quantize_wgt(tensor, bit)
+ *              functions.py:9-23   channel_wise_quantizationperchan(tensor, bit, i)
+ *    (min/max -> fp64 scale, z -> five separately rounded fp32 ops)
+ * ============================================================================================= */
+
+/* Bytes of one packed row: bit 8/6 -> K, 4 -> ceil(K/2), 2 -> ceil(K/4), 16 -> 2K (lo plane, hi plane).
+ * Codes are little-endian inside a byte: element i of a 4-bit row sits in byte i/2, bits 4*(i%2).. */
+SLQ_API int64_t slq_packed_row_bytes(int64_t K, int32_t bit);
+
+/* One launch for a work-list of (row, bit) jobs over ONE contiguous fp32 weight tensor [n_rows, K]
+ * (an OIHW conv weight viewed as rows).  A semilayer is such a list with one bit-width; the whole
+ * model's layers can be issued back to back on the same stream.
+ *   w          in/out  device [n_rows*K] fp32; row rows[j] is overwritten with its de-quantised
+ *                      value when write_back != 0 (the in-place contract of functions.py:22)
+ *   rows, bits in      device [n_jobs] int32   (bit in 1..8)
+ *   codes      out     device blob or NULL; job j's packed codes start at codes + code_offsets[j]
+ *   code_offsets in    device [n_jobs] int64, each a multiple of 4 (ignored when codes == NULL)
+ *   z, s32     out     device [n_jobs] or NULL: zero point (functions.py:40) and float32(scale)
+ *   status     out     device [n_jobs] SLQ_ROW_* flags (required)
+ * Real weight of element i of job j: (code + z[j]) * s32[j].                                     */
+SLQ_API int slq_quantize_rows(float *w, int64_t n_rows, int64_t K, const int32_t *rows, const int32_t *bits,
+                      int32_t n_jobs, int32_t div_mode, int32_t write_back, uint8_t *codes,
+                      const int64_t *code_offsets, int32_t *z, float *s32, int32_t *status,
+                      void *stream);
+
+/* Same operation on HOST buffers (what an FFI caller without device memory binds; also the `e2e`
+ * leg of bench.py): copies w to the device, runs slq_quantize_rows, copies the results back and
+ * synchronises.  Returns SLQ_ERR_ZERO_RANGE if any job hit a constant row (results of the other
+ * jobs are still valid), like the reference's ZeroDivisionError.                                  */
+SLQ_API int slq_quantize_rows_host(float *w, int64_t n_rows, int64_t K, const int32_t *rows,
+                           const int32_t *bits, int32_t n_jobs, int32_t div_mode, int32_t write_back,
+                           uint8_t *codes, const int64_t *code_offsets, int32_t *z, float *s32,
+                           int32_t *status);
+
+/* Content-derived classification used when the forward has to consume weights that were quantised
+ * elsewhere (the mains mutate conv.weight.data and reload fp32 state_dicts):
+ * for every row of w [n_rows, K] find the smallest bit in {2,4,6,8} whose affine grid (spanned by
+ * the row's own min/max) already contains every element; rows that are on no such grid (never
+ * quantised) get bit 16.  Writes bit/z/s per row.  No codes are produced here.                   */
+SLQ_API int slq_classify_rows(const float *w, int64_t n_rows, int64_t K, int32_t *bit, int32_t *z, float *s,
+                      void *stream);
+
+/* Packs rows whose (bit, z, s) are already known (from slq_classify_rows): code = clamp(rint(w/s) - z).
+ * Job j reads row j (all rows, in order).                                                        */
+SLQ_API int slq_encode_rows(const float *w, int64_t n_rows, int64_t K, const int32_t *bit, const int32_t *z,
+                    const float *s, uint8_t *codes, const int64_t *code_offsets, void *stream);
+
+/* =============================================================================================
+ * 2. Quantised convolution = implicit GEMM on tcgen05 (u8 x u8 -> s32 in TMEM) + fused epilogue
+ *    replaces  resnet.py:22-30 nn.Conv2d (called resnet.py:57,60,99,103,107 and the downsample
+ *              convs :63,:111) + native_batch_norm (:58,61,100,104,108) + add_ (:65,:113)
+ *              + relu_ (:59,66,101,105,114)
+ * ============================================================================================= */
+
+#define SLQ_IMPL_UMMA 0 /* TMA + tcgen05.mma kind::i8 + TMEM (the product path) */
+#define SLQ_IMPL_SIMT 1 /* CUDA-core dp4a kernel: on-device cross-check used by tests */
+
+#define SLQ_A_AUTO 0      /* 1x1 stride-1: tiled TMA over [M, Cin]; otherwise im2col TMA */
+#define SLQ_A_IM2COL 1    /* force im2col-mode TMA */
+#define SLQ_A_TILED 2     /* force tiled TMA (1x1 stride-1 pad-0 only) */
+
+#define SLQ_OUT_U8 0  /* u8 NHWC, re-quantised with act_scales[out_id] (the inference path) */
+#define SLQ_OUT_F32 1 /* fp32 NHWC after BN/residual/ReLU (calibration pass) */
+#define SLQ_OUT_ACC 2 /* raw s32 accumulators (parity tests): out[M, Cout] (w16: [M, 2*Cout], low
+                         limb block then high limb block) and window sums out_S[M] */
+#define SLQ_OUT_S8 3  /* s8 NHWC with scale absmax/127: tensors that are not post-ReLU, i.e. the
+                         downsample branch bn(conv1x1(x)) of resnet.py:63/:111 */
+
+typedef struct slq_conv_desc {
+  int32_t N, H, W, Cin;              /* input activations: u8 NHWC */
+  int32_t Cout, kh, kw, stride, pad; /* cross-correlation, no bias, groups=1, dilation=1 */
+  int32_t w16;                       /* 0: 8-bit codes (one limb); 1: 16-bit codes (two u8 limbs) */
+  int32_t impl;                      /* SLQ_IMPL_* */
+  int32_t a_mode;                    /* SLQ_A_* */
+} slq_conv_desc;
+
+typedef struct slq_conv slq_conv; /* opaque: tensor maps + launch geometry of one layer */
+
+/* Rows of the GEMM-ready weight matrix for a layer and its K extent (= kh*kw*Cin). */
+SLQ_API int64_t slq_gemm_weight_rows(const slq_conv_desc *d);
+
+/* Builds the GEMM-ready B operand from the packed per-row store:
+ *   wg [slq_gemm_weight_rows(d), kh*kw*Cin] u8, K ordered (r, s, c) to match NHWC activations.
+ *   w8 : row oc = codes of channel oc (bit <= 8 rows, 2/4-bit rows unpacked), zero rows up to a
+ *        multiple of the N tile.
+ *   w16: per 64-channel tile t, rows [128t, 128t+64) = low limbs, [128t+64, 128t+128) = high limbs.
+ * packed rows are in OIHW order (c, r, s) as slq_quantize_rows / slq_encode_rows wrote them.      */
+SLQ_API int slq_build_gemm_weights(const slq_conv_desc *d, const uint8_t *codes, const int64_t *code_offsets,
+                           const int32_t *bit, uint8_t *wg, void *stream);
+
+SLQ_API int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const uint8_t *wg, slq_conv **out);
+SLQ_API void slq_conv_destroy(slq_conv *c);
+
+typedef struct slq_epilogue {
+  const float *wscale;     /* [Cout] s32[oc] * bn_a[oc]   (bn_a = gamma / sqrt(var + eps))        */
+  const float *zf;         /* [Cout] (float) z[oc]                                                 */
+  const float *bias;       /* [Cout] bn_b[oc] = beta - mean * bn_a                                 */
+  const float *act_scales; /* device array of per-tensor activation scales                        */
+  int32_t in_id, out_id, res_id; /* indices into act_scales; res_id < 0: no residual              */
+  const uint8_t *res;      /* [M, Cout] NHWC residual (block identity) or NULL                    */
+  int32_t res_signed;      /* 0: res is u8 (a post-ReLU tensor); 1: s8 (a SLQ_OUT_S8 tensor)       */
+  void *out;               /* see SLQ_OUT_*                                                        */
+  int32_t *out_S;          /* SLQ_OUT_ACC only: [M] window sums, may be NULL                       */
+  int32_t out_mode;
+  int32_t relu;
+} slq_epilogue;
+
+/* y[m, oc] = (acc[m,oc] + z[oc] * S[m]) * wscale[oc] * act_scales[in_id] + bias[oc]
+ *            (+ res[m,oc] * act_scales[res_id]) ; ReLU ; u8 = clamp(rint(y / act_scales[out_id])) */
+SLQ_API int slq_conv_launch(slq_conv *c, const slq_epilogue *e, void *stream);
+
+/* =============================================================================================
+ * 3. Un-quantised ends of the network and calibration helpers
+ * ============================================================================================= */
+
+/* Stem: resnet.py:206-209  conv1 7x7 s2 p3 (3->64, fp32 weights) + bn1 + relu + maxpool 3x3 s2 p1.
+ * x fp32 NCHW [N,3,H,W] -> out NHWC [N,Hp,Wp,64], Hp = ((H+1)/2+1)/2 (u8 via act_scales[out_id], or
+ * fp32 when out_mode == SLQ_OUT_F32).  `scratch` holds the pre-pool activations:
+ * N*Hc*Wc*64 floats with Hc = (H+1)/2.                                                          */
+SLQ_API int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W, const float *w,
+                     const float *bn_a, const float *bn_b, const float *act_scales, int32_t out_id,
+                     float *scratch, void *out, int32_t out_mode, void *stream);
+
+/* Tail: resnet.py:216-218  adaptive_avg_pool2d((1,1)) + flatten + fc (fp32 weights + bias).
+ * x u8 NHWC [N, HW, C] -> logits fp32 [N, O]; pooled is scratch [N, C] fp32.                     */
+SLQ_API int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C, const float *act_scales,
+                     int32_t in_id, const float *fc_w, const float *fc_b, int32_t O, float *pooled,
+                     float *logits, void *stream);
+
+/* Calibration of the static per-tensor activation scales (the reference never quantises
+ * activations; this path must): act_scales[id] = max|y| / qmax (1.0 if max == 0),
+ * qmax = 255 for post-ReLU (u8) tensors, 127 for signed (s8) ones.
+ * `tmp` is one device uint32 of scratch, zeroed by the call.                                     */
+SLQ_API int slq_absmax_scale(const float *y, int64_t n, float *act_scales, int32_t id, int32_t qmax,
+                     uint32_t *tmp, void *stream);
+/* out[i] = clamp(rint(y[i] / act_scales[id]), 0, 255)  (is_signed: clamp to [-127, 127], s8) */
+SLQ_API int slq_quantize_act(const float *y, int64_t n, const float *act_scales, int32_t id,
+                     int32_t is_signed, uint8_t *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLQ_H_ */

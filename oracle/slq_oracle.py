@@ -1,0 +1,243 @@
+"""oracle/slq_oracle.py -- TEST INFRASTRUCTURE ONLY (the checker; never the thing shipped or timed,
+except as bench.py's cpu_baseline / --impl reference leg).
+
+CPU restatements used by tests/, __graft_entry__.smoke() and bench.py's CPU leg:
+
+* quantizer  : ctypes wrapper over oracle/quant_oracle.c, a C restatement of the reference's
+               functions.py:25-43 (quantize_wgt) / :9-23 (channel_wise_quantizationperchan).
+* fp32 forward: ``torch_forward`` -- the reference's hot path IS stock torch.nn modules
+               (resnet.py:204-220 -> aten::convolution / native_batch_norm / relu_ / add_), a
+               third-party dependency that is not vendored under /root/reference; the installed
+               torch (2.11.0) is that arithmetic, restated here call-for-call with
+               torch.nn.functional on the module tree's tensors.
+* integer pipeline: numpy restatement of THIS repo's u8 x u8 -> s32 implicit-GEMM convolution and
+               fused epilogue so that the CUDA kernels' integer accumulators
+               and u8 activations can be checked bit-for-bit at small sizes.
+
+Parity pin: tests/test_oracle_pins.py checks the quantizer and the fp32 forward against
+tests/golden/*.npz, produced by oracle/gen_golden.py from the unmodified reference run in the build
+container.  The reference itself ships no tests or golden vectors.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libslq_oracle.so")
+        if not os.path.exists(path):
+            build()
+        lib = ctypes.CDLL(path)
+        lib.slq_oracle_quantize_row.restype = ctypes.c_int
+        lib.slq_oracle_quantize_row.argtypes = [
+            ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _LIB = lib
+    return _LIB
+
+
+DIV_TRUE = 0    # ATen CPU: true fp32 divide
+DIV_RECIP = 1   # ATen CUDA: multiply by fp32 reciprocal of the (CPU-scalar) divisor
+
+ST_OK, ST_ZERO_RANGE, ST_CODE_RANGE = 0, 1, 2
+
+
+def quantize_row(w, bit, div_mode=DIV_TRUE):
+    """functions.py:25-43.  Returns (q fp32[K], codes int32[K], z int, s32 np.float32, status)."""
+    w = np.ascontiguousarray(w, dtype=np.float32).reshape(-1)
+    K = w.size
+    q = np.empty(K, np.float32)
+    codes = np.empty(K, np.int32)
+    z = ctypes.c_int32(0)
+    s32 = ctypes.c_float(0)
+    s64 = ctypes.c_double(0)
+    st = _lib().slq_oracle_quantize_row(
+        w.ctypes.data, K, int(bit), int(div_mode), q.ctypes.data, codes.ctypes.data,
+        ctypes.byref(z), ctypes.byref(s32), ctypes.byref(s64))
+    if st == ST_ZERO_RANGE:
+        raise ZeroDivisionError("float division by zero")  # functions.py:40 behaviour
+    return q, codes, int(z.value), np.float32(s32.value), st
+
+
+def channel_wise(tensor2d, bit, i, div_mode=DIV_TRUE):
+    """functions.py:9-23 on a numpy [rows, K] fp32 array, in place."""
+    q, _, _, _, _ = quantize_row(tensor2d[i], bit, div_mode)
+    tensor2d[i] = q
+    return tensor2d
+
+
+# ----------------------------------------------------------------------------------------------
+# storage format of the codes: little-endian bit packing inside a byte
+# ----------------------------------------------------------------------------------------------
+def packed_row_bytes(K, bit):
+    if bit == 16:
+        return 2 * K
+    if bit in (8, 6):
+        return K
+    if bit == 4:
+        return (K + 1) // 2
+    if bit == 2:
+        return (K + 3) // 4
+    raise ValueError(bit)
+
+
+def pack_codes(codes, bit):
+    c = np.asarray(codes).astype(np.int64).reshape(-1)
+    K = c.size
+    if bit in (8, 6):
+        return c.astype(np.uint8)
+    if bit == 16:  # low-limb plane then high-limb plane
+        return np.concatenate([(c & 255).astype(np.uint8), (c >> 8).astype(np.uint8)])
+    per = 8 // bit
+    pad = (-K) % per
+    c = np.concatenate([c, np.zeros(pad, np.int64)]).reshape(-1, per)
+    out = np.zeros(c.shape[0], np.int64)
+    for j in range(per):
+        out |= c[:, j] << (bit * j)
+    return out.astype(np.uint8)
+
+
+def unpack_codes(packed, K, bit):
+    p = np.asarray(packed, dtype=np.uint8).astype(np.int64)
+    if bit in (8, 6):
+        return p[:K].astype(np.int32)
+    if bit == 16:
+        return (p[:K] | (p[K:2 * K] << 8)).astype(np.int32)
+    per = 8 // bit
+    cols = [(p >> (bit * j)) & ((1 << bit) - 1) for j in range(per)]
+    return np.stack(cols, 1).reshape(-1)[:K].astype(np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# content-derived encoder: smallest b in {2,4,6,8} for which the fp32 row
+# already lies on the b-bit affine grid spanned by its own min/max; otherwise a 16-bit grid.
+# ----------------------------------------------------------------------------------------------
+ENCODE_TOL = np.float32(0.02)
+
+
+def encode_row(w):
+    """Returns (bit, codes int32[K], z int, s np.float32).  real weight ~= (codes + z) * s."""
+    w = np.ascontiguousarray(w, dtype=np.float32).reshape(-1)
+    mn, mx = np.float32(w.min()), np.float32(w.max())
+    if mx == mn:
+        if mn == 0:
+            return 16, np.zeros(w.size, np.int32), 0, np.float32(1.0)
+        return 16, np.zeros(w.size, np.int32), 1, mn
+    for bit in (2, 4, 6, 8, 16):
+        levels = (1 << bit) - 1
+        scale = (float(mx) - float(mn)) / levels
+        s32 = np.float32(scale)
+        if s32 == 0 or not np.isfinite(np.float32(1.0) / s32):
+            continue
+        zd = float(np.rint(float(mn) / scale))
+        if abs(zd) > 1.0e6:
+            continue
+        zf = np.float32(zd)
+        t = (w / s32).astype(np.float32)
+        r = np.rint(t).astype(np.float32)
+        if bit != 16:
+            if np.max(np.abs(t - r)) > ENCODE_TOL:
+                continue
+        u = (r - zf).astype(np.float32)
+        u = np.minimum(np.maximum(u, np.float32(0)), np.float32(levels))
+        return bit, u.astype(np.int32), int(zd), s32
+    # degenerate range (denormal scale): represent exactly nothing better than a constant row
+    return 16, np.zeros(w.size, np.int32), 1, mn if mn != 0 else np.float32(1.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# integer implicit-GEMM convolution + fused epilogue of this repo's pipeline (numpy, exact)
+# ----------------------------------------------------------------------------------------------
+def im2col_nhwc(x, kh, kw, stride, pad):
+    """x [N,H,W,C] -> A [N*Ho*Wo, kh*kw*C] with K ordered (r, s, c); zero padding."""
+    N, H, W, C = x.shape
+    Ho = (H + 2 * pad - kh) // stride + 1
+    Wo = (W + 2 * pad - kw) // stride + 1
+    xp = np.zeros((N, H + 2 * pad, W + 2 * pad, C), x.dtype)
+    xp[:, pad:pad + H, pad:pad + W, :] = x
+    cols = []
+    for r in range(kh):
+        for s in range(kw):
+            cols.append(xp[:, r:r + stride * Ho:stride, s:s + stride * Wo:stride, :])
+    A = np.concatenate(cols, axis=3).reshape(N * Ho * Wo, kh * kw * C)
+    return A, Ho, Wo
+
+
+def conv_acc(x_u8, codes_ohwi, stride, pad):
+    """Exact integer accumulators.  x_u8 [N,H,W,C] uint8; codes_ohwi [Cout,kh,kw,C] ints >= 0.
+    Returns (acc int64 [M,Cout], S int64 [M], Ho, Wo): acc = sum x*u, S = window sum of x."""
+    Cout, kh, kw, C = codes_ohwi.shape
+    A, Ho, Wo = im2col_nhwc(x_u8.astype(np.int64), kh, kw, stride, pad)
+    B = codes_ohwi.reshape(Cout, kh * kw * C).astype(np.int64)
+    return A @ B.T, A.sum(1), Ho, Wo
+
+
+def epilogue(acc, S, zf, wscale, bias, s_in, res_u8=None, s_res=None, relu=True):
+    """fp32 epilogue exactly as csrc/epilogue.cuh computes it (separately rounded mul/add):
+       v = f32(acc) + zf*f32(S);  y = (v*(wscale*s_in)) + bias;  y += f32(res)*s_res;  relu."""
+    f = np.float32
+    accf = acc.astype(np.float32)
+    Sf = S.astype(np.float32)[:, None]
+    v = (accf + (zf.astype(f)[None, :] * Sf).astype(f)).astype(f)
+    sc = (wscale.astype(f) * f(s_in)).astype(f)
+    y = ((v * sc[None, :]).astype(f) + bias.astype(f)[None, :]).astype(f)
+    if res_u8 is not None:
+        y = (y + (res_u8.astype(f) * f(s_res)).astype(f)).astype(f)
+    if relu:
+        y = np.maximum(y, f(0))
+    return y
+
+
+def requant_u8(y, s_out):
+    inv = np.float32(1.0) / np.float32(s_out)
+    q = np.rint((y * inv).astype(np.float32))
+    return np.clip(q, 0, 255).astype(np.uint8)
+
+
+def act_scale_from_absmax(amax):
+    amax = np.float32(amax)
+    return np.float32(1.0) if amax == 0 else np.float32(amax / np.float32(255.0))
+
+
+# ----------------------------------------------------------------------------------------------
+# fp32 forward of the reference model (resnet.py:204-220) restated on a module tree's tensors
+# ----------------------------------------------------------------------------------------------
+def torch_forward(net, x):
+    """Stock-torch fp32 forward of a ResNet-shaped module tree (reference resnet.py:204-220,
+    BasicBlock :55-68, Bottleneck :97-116).  Works for the reference's modules and for this
+    repo's resnet.py mirror alike (same attribute names).  eval-mode BatchNorm."""
+    import torch
+    import torch.nn.functional as F
+
+    def bn(m, t):
+        return F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, m.eps)
+
+    def conv(m, t):
+        return F.conv2d(t, m.weight, None, m.stride, m.padding)
+
+    with torch.no_grad():
+        t = F.relu(bn(net.bn1, conv(net.conv1, x)))
+        t = F.max_pool2d(t, 3, 2, 1)
+        for stage in (net.layer1, net.layer2, net.layer3, net.layer4):
+            for blk in stage:
+                idt = t
+                o = F.relu(bn(blk.bn1, conv(blk.conv1, t)))
+                o = bn(blk.bn2, conv(blk.conv2, o))
+                if hasattr(blk, "conv3"):
+                    o = bn(blk.bn3, conv(blk.conv3, F.relu(o)))
+                if blk.downsample is not None:
+                    idt = bn(blk.downsample[1], conv(blk.downsample[0], t))
+                t = F.relu(o + idt)
+        t = torch.flatten(F.adaptive_avg_pool2d(t, (1, 1)), 1)
+        return F.linear(t, net.fc.weight, net.fc.bias)

@@ -1,0 +1,585 @@
+// csrc/conv_umma.cu -- quantised convolution as an implicit GEMM on Blackwell tensor cores.
+//
+// Replaces aten::convolution + native_batch_norm + add_ + relu_ of the reference's residual blocks
+// (resnet.py:55-68 BasicBlock.forward, :97-116 Bottleneck.forward; conv modules resnet.py:22-30).
+//
+//   D[m, oc] = sum_k A[m, k] * B[oc, k]         u8 x u8 -> s32, tcgen05.mma kind::i8, D in TMEM
+//   A = NHWC u8 activations, gathered by TMA: im2col-mode tensor map for 3x3 / strided layers
+//       (zero padding and the (r,s) filter offsets are resolved by the TMA unit), tiled map for
+//       1x1 stride-1 layers;  B = GEMM-ready weight codes [rows, K], K ordered (r, s, c).
+//   One extra "ones" B row per tile makes the tensor core also produce the window sum
+//   S[m] = sum_k A[m, k] that the zero-point correction z[oc]*S[m] needs.
+//
+// Persistent, warp-specialised CTA (256 threads, 1 CTA/SM):
+//   warp 0   TMA producer           (one lane)   smem ring of kStages x {A 128xSWZ, B (bn+16)xSWZ}
+//   warp 1   tcgen05.mma issuer     (one lane)   accumulators double-buffered in TMEM (2 x 256 cols)
+//   warp 2   TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> de-quantise + folded BN + residual + ReLU -> u8 NHWC store
+#include <algorithm>
+#include <new>
+
+#include "conv_common.cuh"
+
+namespace slq {
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
+      printf("slq conv_umma: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                                   int c, int w, int h, int n, uint16_t off_w,
+                                                   uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], 8-bit integer operands, single CTA
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  return v;
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major shared-memory matrix descriptor for a tile whose rows are SWZ bytes long and stored with
+// the SWZ-byte TMA/UMMA swizzle (8-row groups of 8*SWZ bytes, tile base aligned to 1024 B).
+template <int SWZ>
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  constexpr uint64_t kLayout = (SWZ == 128) ? 2 : 4;  // SWIZZLE_128B / SWIZZLE_64B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address  [0,14)
+  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((8 * SWZ) >> 4) << 32;      // stride byte offset: next 8-row group
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= kLayout << 61;
+  return d;
+}
+
+template <int SWZ>
+struct Cfg {
+  static constexpr int kStages = (SWZ == 128) ? 6 : 8;
+  static constexpr int kABytes = kTileM * SWZ;
+  static constexpr int kBRows = 128 + 16;  // bn_cols (<=128) + 16 rows for the ones-row group
+  static constexpr int kBBytes = kBRows * SWZ;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kParamBytes = 128 * 16;  // float4 {wscale*s_in, zf, bias, -} per channel
+  static constexpr int kBarBytes = 256;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kParamBytes + kBarBytes;
+  static_assert(kStageBytes % 1024 == 0, "stage must keep 1024B alignment");
+};
+
+struct KernelArgs {
+  ConvGeom g;
+  EpiDev e;
+  int a_im2col;
+  int num_kb;         // K blocks per tile = kh*kw*Cin / SWZ
+  int chunks_per_tap; // Cin / SWZ
+  long long m_tiles;
+};
+
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
+constexpr int kTmemCols = 512;
+
+template <int SWZ, bool W16>
+__global__ void __launch_bounds__(256, 1)
+conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const KernelArgs a) {
+  using C = Cfg<SWZ>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  float4 *prm = reinterpret_cast<float4 *>(smem + C::kStages * C::kStageBytes);
+  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes + C::kParamBytes;
+  // barrier slots (8 bytes each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 2 + b); };
+  volatile uint32_t *tmem_slot =
+      reinterpret_cast<volatile uint32_t *>(smem + C::kStages * C::kStageBytes + C::kParamBytes + 8 * (2 * C::kStages + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvGeom &g = a.g;
+  const int bn_cols = g.bn_cols;
+  const int umma_n = bn_cols + 16;
+  const long long total_tiles = a.m_tiles * g.n_tiles;
+
+  // ---- one-time setup -----------------------------------------------------------------------
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void *)tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // constant "ones" row group behind the TMA-written B rows of every stage:
+  // row bn_cols = 0x01.., rows bn_cols+1 .. +15 = 0  (identical bytes are swizzle-invariant)
+  for (int i = threadIdx.x; i < C::kStages * 16 * (SWZ / 16); i += blockDim.x) {
+    const int s = i / (16 * (SWZ / 16));
+    const int rem = i % (16 * (SWZ / 16));
+    const int row = rem / (SWZ / 16), chunk = rem % (SWZ / 16);
+    uint4 v = row == 0 ? make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u) : make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4 *>(smem + s * C::kStageBytes + C::kABytes + (bn_cols + row) * SWZ + chunk * 16) = v;
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ============================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = (uint32_t)(C::kABytes + bn_cols * SWZ);
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const long long m_tile = tile / g.n_tiles;
+        const int n_tile = (int)(tile % g.n_tiles);
+        const long long m0 = m_tile * kTileM;
+        int cw = 0, chh = 0, cn = 0;
+        if (a.a_im2col) {
+          const int q = (int)(m0 % g.Wo);
+          const int p = (int)((m0 / g.Wo) % g.Ho);
+          cn = (int)(m0 / ((long long)g.Wo * g.Ho));
+          cw = q * g.stride - g.pad;
+          chh = p * g.stride - g.pad;
+        }
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint32_t sb = sa + C::kABytes;
+          mbar_expect_tx(full_bar(stage), tx_bytes);
+          const int tap = kb / a.chunks_per_tap;
+          const int cchunk = kb - tap * a.chunks_per_tap;
+          if (a.a_im2col) {
+            const int r = tap / g.kw, s = tap - r * g.kw;
+            tma_load_im2col_4d(sa, &tmA, full_bar(stage), cchunk * SWZ, cw, chh, cn, (uint16_t)s, (uint16_t)r);
+          } else {
+            tma_load_2d(sa, &tmA, full_bar(stage), cchunk * SWZ, (int)m0);
+          }
+          tma_load_2d(sb, &tmB, full_bar(stage), kb * SWZ, n_tile * bn_cols);
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==============================================
+    if (lane == 0) {
+      // instruction descriptor: D=s32, A=B=u8, both K-major, M=128, N=umma_n
+      const uint32_t idesc = (2u << 4) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(tempty_bar(buf), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + buf * kAccStride;
+        for (int kb = 0; kb < a.num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * C::kStageBytes;
+          const uint64_t da = make_smem_desc<SWZ>(sa);
+          const uint64_t db = make_smem_desc<SWZ>(sa + C::kABytes);
+#pragma unroll
+          for (int k = 0; k < SWZ / 32; ++k)  // UMMA_K = 32 bytes of K per instruction
+            umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ================================================
+    const EpiDev &e = a.e;
+    const int wq = warp & 3;  // TMEM lane quarter this warp may touch
+    const int et = threadIdx.x - 128;
+    const bool has_res = e.res != nullptr;
+    float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
+    if (e.out_mode != SLQ_OUT_ACC) {
+      s_in = e.act_scales[e.in_id];
+      if (has_res) s_res = e.act_scales[e.res_id];
+      if (e.out_mode != SLQ_OUT_F32) inv_out = __fdiv_rn(1.0f, e.act_scales[e.out_id]);
+    }
+    const int chunks = g.bn_ch / 32;
+    long long it = 0;
+    int last_n_tile = -1;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const long long m_tile = tile / g.n_tiles;
+      const int n_tile = (int)(tile % g.n_tiles);
+      const int buf = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      if (n_tile != last_n_tile && e.out_mode != SLQ_OUT_ACC) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
+        if (et < g.bn_ch) {
+          const int oc = n_tile * g.bn_ch + et;
+          float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (oc < g.Cout) p = make_float4(__fmul_rn(e.wscale[oc], s_in), e.zf[oc], e.bias[oc], 0.f);
+          prm[et] = p;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        last_n_tile = n_tile;
+      }
+      mbar_wait(tfull_bar(buf), acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * kAccStride;
+      const long long m = m_tile * kTileM + wq * 32 + lane;
+      const bool valid = m < g.M;
+      const uint32_t S_raw = tmem_ld1(trow + bn_cols);
+      tmem_ld_wait();
+      const float Sf = (float)(int)S_raw;
+      if (e.out_mode == SLQ_OUT_ACC && e.out_S && valid && n_tile == 0) e.out_S[m] = (int)S_raw;
+      for (int ch = 0; ch < chunks; ++ch) {
+        uint32_t lo[32], hi[32];
+        tmem_ld32(trow + ch * 32, lo);
+        if (W16) tmem_ld32(trow + 64 + ch * 32, hi);
+        tmem_ld_wait();
+        const int cb = n_tile * g.bn_ch + ch * 32;  // first output channel of this chunk
+        if (!valid || cb >= g.Cout) continue;
+        if (e.out_mode == SLQ_OUT_ACC) {
+          const long long ld = (long long)(W16 ? 2 : 1) * g.Cout;
+          int4 *o = reinterpret_cast<int4 *>(reinterpret_cast<int32_t *>(e.out) + m * ld + cb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = make_int4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          if (W16) {
+            int4 *oh = reinterpret_cast<int4 *>(reinterpret_cast<int32_t *>(e.out) + m * ld + g.Cout + cb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) oh[j] = make_int4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+          }
+          continue;
+        }
+        uint32_t rw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (has_res) {
+          const uint4 *rp = reinterpret_cast<const uint4 *>(e.res + m * g.Cout + cb);
+          const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w;
+          rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+        }
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float4 p = prm[ch * 32 + j];
+          float v = epi_value((int)lo[j], W16 ? (int)hi[j] : 0, W16, Sf, p.y, p.x, p.z);
+          const int rraw = (int)((rw[j >> 2] >> (8 * (j & 3))) & 255u);
+          y[j] = epi_residual_relu(v, has_res, rraw, e.res_signed != 0, s_res, e.relu != 0);
+        }
+        if (e.out_mode == SLQ_OUT_F32) {
+          float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.out) + m * g.Cout + cb);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        } else {
+          uint32_t pk[8];
+          const bool sgn = e.out_mode == SLQ_OUT_S8;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b)
+              w |= (sgn ? epi_quant_s8(y[4 * j + b], inv_out) : epi_quant_u8(y[4 * j + b], inv_out)) << (8 * b);
+            pk[j] = w;
+          }
+          uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(e.out) + m * g.Cout + cb);
+          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(tempty_bar(buf));  // 128 arrivals release the accumulator buffer
+    }
+  }
+
+  // ---- teardown -----------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int get_encoders(EncodeTiledFn *tiled, EncodeIm2colFn *im2col) {
+  static EncodeTiledFn f_tiled = nullptr;
+  static EncodeIm2colFn f_im2col = nullptr;
+  if (!f_tiled || !f_im2col) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    SLQ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+    if (qr != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return SLQ_ERR_CUDA;
+    }
+    f_tiled = (EncodeTiledFn)p;
+    p = nullptr;
+    SLQ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &qr));
+    if (qr != cudaDriverEntryPointSuccess || !p) {
+      set_error("cuTensorMapEncodeIm2col not available from the driver");
+      return SLQ_ERR_CUDA;
+    }
+    f_im2col = (EncodeIm2colFn)p;
+  }
+  *tiled = f_tiled;
+  *im2col = f_im2col;
+  return SLQ_OK;
+}
+
+static int build_tensor_maps(slq_conv *c) {
+  EncodeTiledFn enc_tiled;
+  EncodeIm2colFn enc_im2col;
+  int rc = get_encoders(&enc_tiled, &enc_im2col);
+  if (rc != SLQ_OK) return rc;
+  const ConvGeom &g = c->g;
+  const int swz = c->swizzle;
+  const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r;
+  {  // B: GEMM-ready weights [gemm_rows, Ktot] u8, box = SWZ bytes of K x bn_cols rows
+    cuuint64_t dims[2] = {(cuuint64_t)g.Ktot, (cuuint64_t)g.gemm_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)g.Ktot};
+    cuuint32_t box[2] = {(cuuint32_t)swz, (cuuint32_t)g.bn_cols};
+    cuuint32_t es[2] = {1, 1};
+    r = enc_tiled(&c->tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)c->wg, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(B) failed: CUresult %d", (int)r);
+      return SLQ_ERR_CUDA;
+    }
+  }
+  if (!c->a_im2col) {  // A: [M, Cin] u8 (1x1 stride-1), box = SWZ channels x 128 pixels
+    cuuint64_t dims[2] = {(cuuint64_t)g.Cin, (cuuint64_t)g.M};
+    cuuint64_t strides[1] = {(cuuint64_t)g.Cin};
+    cuuint32_t box[2] = {(cuuint32_t)swz, (cuuint32_t)kTileM};
+    cuuint32_t es[2] = {1, 1};
+    r = enc_tiled(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)c->in, dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(A) failed: CUresult %d", (int)r);
+      return SLQ_ERR_CUDA;
+    }
+  } else {  // A: NHWC u8 through im2col mode; base pixel = top-left tap of each output pixel
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cin, (cuuint64_t)g.W * g.Cin, (cuuint64_t)g.H * g.W * g.Cin};
+    int lower[2] = {-g.pad, -g.pad};                               // {W, H}
+    int upper[2] = {g.pad - (g.kw - 1), g.pad - (g.kh - 1)};       // {W, H}
+    cuuint32_t es[4] = {1, (cuuint32_t)g.stride, (cuuint32_t)g.stride, 1};
+    r = enc_im2col(&c->tmA, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, (void *)c->in, dims, strides, lower, upper,
+                   (cuuint32_t)swz, (cuuint32_t)kTileM, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeIm2col(A) failed: CUresult %d", (int)r);
+      return SLQ_ERR_CUDA;
+    }
+    // Known driver issue (<= 13.1): im2col maps of tensors below 128 KiB come back with bit 21 of
+    // the second descriptor word set and then fault; CUTLASS clears it the same way.
+    int drv = 0;
+    if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010 &&
+        (long long)g.N * g.H * g.W * g.Cin < 131072)
+      reinterpret_cast<uint64_t *>(&c->tmA)[1] &= ~(1ull << 21);
+  }
+  return SLQ_OK;
+}
+
+template <int SWZ, bool W16>
+static int launch_umma(slq_conv *c, const EpiDev &e, cudaStream_t st) {
+  using C = Cfg<SWZ>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SLQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<SWZ, W16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  C::kSmemBytes));
+    attr_done = true;
+  }
+  KernelArgs a;
+  a.g = c->g;
+  a.e = e;
+  a.a_im2col = c->a_im2col;
+  a.chunks_per_tap = c->g.Cin / SWZ;
+  a.num_kb = c->g.kh * c->g.kw * a.chunks_per_tap;
+  a.m_tiles = ceil_div(c->g.M, kTileM);
+  conv_umma_kernel<SWZ, W16><<<c->num_ctas, 256, C::kSmemBytes, st>>>(c->tmA, c->tmB, a);
+  SLQ_LAUNCH_CHECK();
+  return SLQ_OK;
+}
+
+}  // namespace slq
+
+using namespace slq;
+
+extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const uint8_t *wg, slq_conv **out) {
+  int rc = validate_desc(d);
+  if (rc != SLQ_OK) return rc;
+  SLQ_CHECK_ARG(in && wg && out, "slq_conv_create: null pointer argument");
+  SLQ_CHECK_ARG(d->impl == SLQ_IMPL_UMMA || d->impl == SLQ_IMPL_SIMT, "slq_conv_create: impl %d", d->impl);
+  SLQ_CHECK_ARG(reinterpret_cast<uintptr_t>(in) % 16 == 0 && reinterpret_cast<uintptr_t>(wg) % 16 == 0,
+                "slq_conv_create: buffers must be 16-byte aligned");
+  slq_conv *c = new (std::nothrow) slq_conv();
+  SLQ_CHECK_ARG(c != nullptr, "slq_conv_create: out of host memory");
+  c->desc = *d;
+  c->g = make_geom(*d);
+  c->in = in;
+  c->wg = wg;
+  c->swizzle = (d->Cin % 128 == 0) ? 128 : 64;
+  const bool can_tile = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0;
+  if (d->a_mode == SLQ_A_TILED && !can_tile) {
+    delete c;
+    set_error("slq_conv_create: SLQ_A_TILED needs a 1x1 stride-1 layer");
+    return SLQ_ERR_INVALID;
+  }
+  c->a_im2col = (d->a_mode == SLQ_A_IM2COL) ? 1 : (d->a_mode == SLQ_A_TILED ? 0 : (can_tile ? 0 : 1));
+  if (d->impl == SLQ_IMPL_UMMA) {
+    if (d->Cout % 64 != 0) {
+      delete c;
+      set_error("slq_conv_create: the tcgen05 path needs Cout %% 64 == 0 (got %d)", d->Cout);
+      return SLQ_ERR_UNSUPPORTED;
+    }
+    rc = build_tensor_maps(c);
+    if (rc != SLQ_OK) {
+      delete c;
+      return rc;
+    }
+    const long long tiles = ceil_div(c->g.M, kTileM) * c->g.n_tiles;
+    c->num_ctas = (int)std::min<long long>(tiles, sm_count());
+    c->smem_bytes = c->swizzle == 128 ? Cfg<128>::kSmemBytes : Cfg<64>::kSmemBytes;
+  }
+  *out = c;
+  return SLQ_OK;
+}
+
+extern "C" void slq_conv_destroy(slq_conv *c) { delete c; }
+
+extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream) {
+  SLQ_CHECK_ARG(c && ep, "slq_conv_launch: null handle/epilogue");
+  SLQ_CHECK_ARG(ep->out != nullptr, "slq_conv_launch: out is NULL");
+  SLQ_CHECK_ARG(ep->out_mode >= SLQ_OUT_U8 && ep->out_mode <= SLQ_OUT_S8, "slq_conv_launch: out_mode %d", ep->out_mode);
+  if (ep->out_mode != SLQ_OUT_ACC) {
+    SLQ_CHECK_ARG(ep->wscale && ep->zf && ep->bias && ep->act_scales, "slq_conv_launch: epilogue vectors missing");
+    SLQ_CHECK_ARG(!ep->res || ep->res_id >= 0, "slq_conv_launch: residual without res_id");
+  }
+  SLQ_CHECK_ARG(reinterpret_cast<uintptr_t>(ep->out) % 16 == 0 &&
+                    (!ep->res || reinterpret_cast<uintptr_t>(ep->res) % 16 == 0),
+                "slq_conv_launch: out/res must be 16-byte aligned");
+  EpiDev e;
+  e.wscale = ep->wscale; e.zf = ep->zf; e.bias = ep->bias; e.act_scales = ep->act_scales;
+  e.res = ep->res; e.out = ep->out; e.out_S = ep->out_S;
+  e.in_id = ep->in_id; e.out_id = ep->out_id; e.res_id = ep->res_id;
+  e.out_mode = ep->out_mode; e.relu = ep->relu; e.res_signed = ep->res_signed;
+  e.Cout = c->g.Cout; e.w16 = c->g.w16; e.M = c->g.M;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (c->desc.impl == SLQ_IMPL_SIMT) return launch_conv_simt(c->g, c->in, c->wg, e, st);
+  if (c->swizzle == 128)
+    return c->g.w16 ? launch_umma<128, true>(c, e, st) : launch_umma<128, false>(c, e, st);
+  return c->g.w16 ? launch_umma<64, true>(c, e, st) : launch_umma<64, false>(c, e, st);
+}

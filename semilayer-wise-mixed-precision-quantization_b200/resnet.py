@@ -1,0 +1,196 @@
+"""resnet.py -- drop-in mirror of the reference's ``resnet.py`` whose eval-mode CUDA forward runs on
+the B200 engine (slq_engine.Engine: tcgen05 implicit-GEMM convs + fused epilogues) instead of
+aten::convolution / native_batch_norm / relu_ / add_.
+
+Boundary kept exactly:
+  * ``resnet18/34/50(pretrained=False, progress=True, **kwargs)``      reference resnet.py:235-265
+  * module tree ``conv1, bn1, relu, maxpool, layer1..4[b].{conv1,bn1,conv2,bn2,conv3,bn3,relu,
+    downsample}, avgpool, fc`` with torchvision-compatible ``state_dict`` keys   (resnet.py:121-202)
+  * ``.weight`` of every conv is an fp32 Parameter ``[Cout,Cin,kh,kw]`` whose ``.data`` the mains
+    re-assign after ``functions.channel_wise_quantizationperchan``       (resnet50_main.py:191)
+  * ``net(x)``: fp32 NCHW in, fp32 logits out, same device               (resnet.py:204-223)
+  * same construction + init order as the reference, so ``torch.manual_seed(s)`` followed by
+    ``resnetXX(num_classes=1000)`` yields bit-identical parameters (tests/test_host_logic.py).
+
+There is no eager-PyTorch or CPU fallback: a CPU tensor or training-mode call raises.
+"""
+import torch
+import torch.nn as nn
+
+try:
+    from torch.hub import load_state_dict_from_url
+except ImportError:  # pragma: no cover
+    from torch.utils.model_zoo import load_url as load_state_dict_from_url
+
+__all__ = ["ResNet", "resnet18", "resnet34", "resnet50"]
+
+model_urls = {
+    "resnet18": "https://download.pytorch.org/models/resnet18-5c106cde.pth",
+    "resnet34": "https://download.pytorch.org/models/resnet34-333f7ec4.pth",
+    "resnet50": "https://download.pytorch.org/models/resnet50-19c8e357.pth",
+}
+
+# bumped by functions.channel_wise_quantizationperchan & co.: any engine compiled before the bump
+# re-derives its packed weights from the (mutated) fp32 tensors on its next forward
+WEIGHT_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    WEIGHT_EPOCH[0] += 1
+
+
+def _conv(cin, cout, k, stride=1):
+    return nn.Conv2d(cin, cout, kernel_size=k, stride=stride, padding=k // 2, bias=False)
+
+
+class _Block(nn.Module):
+    """One residual block.  ``kernels`` lists the conv kernel sizes of the main branch; the stride
+    sits on the first 3x3 (ResNet v1.5 for Bottleneck, reference resnet.py:71-76)."""
+    expansion = 1
+    kernels = (3, 3)
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        widths = [planes] * (len(self.kernels) - 1) + [planes * self.expansion]
+        cin = inplanes
+        strided = False
+        relu_registered = False
+        for i, (k, cout) in enumerate(zip(self.kernels, widths), 1):
+            s = 1
+            if k == 3 and not strided:
+                s, strided = stride, True
+            setattr(self, "conv%d" % i, _conv(cin, cout, k, s))
+            setattr(self, "bn%d" % i, nn.BatchNorm2d(cout))
+            if self.expansion == 1 and not relu_registered:  # BasicBlock registers relu after bn1
+                self.relu = nn.ReLU(inplace=True)
+                relu_registered = True
+            cin = cout
+        if not relu_registered:
+            self.relu = nn.ReLU(inplace=True)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):  # blocks only run inside ResNet.forward -> engine
+        raise RuntimeError("residual blocks are executed by the B200 engine through ResNet.forward")
+
+
+class BasicBlock(_Block):
+    expansion = 1
+    kernels = (3, 3)
+
+
+class Bottleneck(_Block):
+    expansion = 4
+    kernels = (1, 3, 1)
+
+
+class ResNet(nn.Module):
+    # tests may install a checker (oracle) for CPU tensors; the product never sets this
+    cpu_checker = None
+
+    def __init__(self, block, layers, num_classes=1000):
+        super().__init__()
+        self.block_name = block.__name__
+        self.arch = layers
+        self.inplanes = 64
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        for i, (planes, n) in enumerate(zip((64, 128, 256, 512), layers), 1):
+            setattr(self, "layer%d" % i, self._make_layer(block, planes, n, stride=1 if i == 1 else 2))
+        self.layers = [self.layer1, self.layer2, self.layer3, self.layer4]
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Linear(512 * block.expansion, num_classes)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+        self._slq_engines = {}
+        self._slq_dirty = True
+
+    def _make_layer(self, block, planes, blocks, stride):
+        downsample = None
+        if stride != 1 or self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(_conv(self.inplanes, planes * block.expansion, 1, stride),
+                                       nn.BatchNorm2d(planes * block.expansion))
+        seq = [block(self.inplanes, planes, stride, downsample)]
+        self.inplanes = planes * block.expansion
+        seq += [block(self.inplanes, planes) for _ in range(1, blocks)]
+        return nn.Sequential(*seq)
+
+    # ---- anything that can change parameters invalidates the compiled engines ----------------
+    def slq_invalidate(self):
+        self._slq_dirty = True
+
+    def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float() ...
+        before = self.conv1.weight.data_ptr()
+        out = super()._apply(fn, *a, **k)
+        self._slq_dirty = True
+        if self.conv1.weight.data_ptr() != before:  # storage moved: compiled pointers are stale
+            self._slq_engines = {}
+        return out
+
+    def load_state_dict(self, *a, **k):
+        self._slq_dirty = True
+        return super().load_state_dict(*a, **k)
+
+    def train(self, mode=True):
+        self._slq_dirty = True
+        return super().train(mode)
+
+    def slq_engine(self, x, **kw):
+        """The compiled engine for inputs shaped like x (built on first use)."""
+        import slq_engine
+        key = (x.shape[0], x.shape[2], x.shape[3], x.device.index)
+        eng = self._slq_engines.get(key)
+        if eng is None:
+            eng = slq_engine.Engine(self, x.shape[0], x.shape[2], x.shape[3], x.device, **kw)
+            self._slq_engines = {key: eng}  # one live shape at a time (activation buffers are large)
+            self._slq_dirty = True
+        return eng
+
+    def forward(self, x):
+        if not x.is_cuda:
+            if ResNet.cpu_checker is not None:
+                return ResNet.cpu_checker(self, x)
+            raise RuntimeError("this ResNet runs on the B200 engine: pass a CUDA tensor "
+                               "(there is no CPU / eager fallback)")
+        if self.training:
+            raise RuntimeError("the B200 engine implements the eval-mode forward only; call net.eval()")
+        import slq_engine
+        n = x.shape[0]
+        cap = slq_engine.engine_batch(self, n)
+        if n < cap:  # short last batch of a loader: pad (static scales keep samples independent)
+            xp = x.new_zeros((cap,) + tuple(x.shape[1:]))
+            xp[:n] = x
+        else:
+            xp = x
+        eng = self.slq_engine(xp)
+        if self._slq_dirty or eng.epoch != WEIGHT_EPOCH[0]:
+            eng.refresh_weights()
+            eng.calibrate(xp)
+            eng.epoch = WEIGHT_EPOCH[0]
+            self._slq_dirty = False
+        return eng.forward(xp)[:n].clone()
+
+
+def _resnet(arch, block, layers, pretrained, progress, **kwargs):
+    model = ResNet(block, layers, **kwargs)
+    if pretrained:
+        model.load_state_dict(load_state_dict_from_url(model_urls[arch], progress=progress), strict=False)
+    return model
+
+
+def resnet18(pretrained=False, progress=True, **kwargs):
+    return _resnet("resnet18", BasicBlock, [2, 2, 2, 2], pretrained, progress, **kwargs)
+
+
+def resnet34(pretrained=False, progress=True, **kwargs):
+    return _resnet("resnet34", BasicBlock, [3, 4, 6, 3], pretrained, progress, **kwargs)
+
+
+def resnet50(pretrained=False, progress=True, **kwargs):
+    return _resnet("resnet50", Bottleneck, [3, 4, 6, 3], pretrained, progress, **kwargs)

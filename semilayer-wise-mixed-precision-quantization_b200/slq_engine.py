@@ -1,0 +1,307 @@
+"""slq_engine.py -- host side of the B200 forward: turns a ResNet module tree (resnet.py) into a
+static sequence of kernel launches over the C ABI (slq_lib) and runs it.
+
+Data layout in HBM:
+  * activations: u8 NHWC per tensor, one static fp32 scale per tensor in ``act_scales`` (device
+    array); the downsample branch (not post-ReLU) is s8;
+  * weights: per conv a PackedLayer (bit/z/s32 per output channel + packed 2/4/8/16-bit codes) and
+    the GEMM-ready u8 matrix the tcgen05 kernel streams with TMA;
+  * everything is allocated once per (batch, H, W); a forward is launches only (CUDA-graph safe).
+
+torch is plumbing here (allocation, streams); no torch op touches activations on the hot path.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+import slq_lib as L
+
+
+def engine_batch(net, n):
+    for (N, _h, _w, _d), _eng in getattr(net, "_slq_engines", {}).items():
+        if N >= n:
+            return N
+    return n
+
+
+def _align(v, a):
+    return (v + a - 1) // a * a
+
+
+class PackedLayer:
+    """Packed store of one conv weight [Cout, K]: the mixed-precision model format.
+    real weight of element e of channel oc = (code + z[oc]) * s[oc]."""
+
+    def __init__(self, bits, z, s, offsets, blob, K):
+        self.bits, self.z, self.s, self.offsets, self.blob, self.K = bits, z, s, offsets, blob, K
+
+    @property
+    def nbytes(self):
+        return int(self.blob.numel())
+
+
+def packed_offsets(bits_host, K):
+    """Row start offsets (16-byte aligned) and blob size for rows with the given bit-widths."""
+    lib = L.lib()
+    sizes = np.array([_align(lib.slq_packed_row_bytes(K, int(b)), 16) for b in bits_host], np.int64)
+    offs = np.zeros(len(sizes), np.int64)
+    if len(sizes) > 1:
+        offs[1:] = np.cumsum(sizes)[:-1]
+    return offs, int(sizes.sum())
+
+
+def classify_weights(weights, stream=None):
+    """slq_classify_rows over a list of fp32 [Cout, K] device tensors, one host sync in total.
+    Returns per tensor (bits_dev, z_dev, s_dev, bits_host)."""
+    lib = L.lib()
+    stream = L.current_stream() if stream is None else stream
+    metas = []
+    for w in weights:
+        rows, K = w.shape[0], w[0].numel()
+        bit = torch.empty(rows, dtype=torch.int32, device=w.device)
+        z = torch.empty(rows, dtype=torch.int32, device=w.device)
+        s = torch.empty(rows, dtype=torch.float32, device=w.device)
+        L.check(lib.slq_classify_rows(w.data_ptr(), rows, K, bit.data_ptr(), z.data_ptr(), s.data_ptr(), stream))
+        metas.append((bit, z, s))
+    all_bits = torch.cat([m[0] for m in metas]).cpu().numpy()  # the one sync
+    out, pos = [], 0
+    for (bit, z, s) in metas:
+        n = bit.numel()
+        out.append((bit, z, s, all_bits[pos:pos + n]))
+        pos += n
+    return out
+
+
+def encode_weight(w, bit, z, s, bits_host, stream=None):
+    lib = L.lib()
+    stream = L.current_stream() if stream is None else stream
+    rows, K = w.shape[0], w[0].numel()
+    offs, total = packed_offsets(bits_host, K)
+    offsets = torch.from_numpy(offs).to(w.device)
+    blob = torch.empty(max(total, 16), dtype=torch.uint8, device=w.device)
+    L.check(lib.slq_encode_rows(w.data_ptr(), rows, K, bit.data_ptr(), z.data_ptr(), s.data_ptr(),
+                                blob.data_ptr(), offsets.data_ptr(), stream))
+    return PackedLayer(bit, z, s, offsets, blob, K)
+
+
+class _ConvOp:
+    pass
+
+
+class Engine:
+    def __init__(self, net, N, H, W, device, impl=L.IMPL_UMMA, a_mode=L.A_AUTO):
+        if device.type != "cuda":
+            raise RuntimeError("slq Engine needs a CUDA device")
+        self.lib = L.lib()
+        self.net, self.N, self.H, self.W, self.device = net, N, H, W, device
+        self.impl, self.a_mode = impl, a_mode
+        self.epoch = -1
+        self.kernel_launches = 0
+        with torch.cuda.device(device):
+            self._plan()
+
+    # ------------------------------------------------------------------------------------------
+    def _new_act(self, shape_nhwc, signed=False):
+        self.act.append(torch.empty(shape_nhwc, dtype=torch.uint8, device=self.device))
+        self.act_signed.append(signed)
+        return len(self.act) - 1
+
+    def _plan(self):
+        net, N, dev = self.net, self.N, self.device
+        if not net.conv1.weight.is_cuda:
+            raise RuntimeError("model parameters must live on the CUDA device (call net.to(device))")
+        Hc, Wc = (self.H + 6 - 7) // 2 + 1, (self.W + 6 - 7) // 2 + 1
+        Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
+        self.act, self.act_signed, self.ops = [], [], []
+        self.stem_scratch = torch.empty(N * Hc * Wc * 64, dtype=torch.float32, device=dev)
+        x_id = self._new_act((N, Hp, Wp, 64))
+        h, w = Hp, Wp
+        max_out = N * Hp * Wp * 64
+        for stage in (net.layer1, net.layer2, net.layer3, net.layer4):
+            for blk in stage:
+                convs = [c for c in ("conv1", "conv2", "conv3") if hasattr(blk, c)]
+                res_id, res_signed = x_id, False
+                cur, ch, cw = x_id, h, w
+                pending = []
+                for i, cname in enumerate(convs):
+                    conv, bn = getattr(blk, cname), getattr(blk, "bn%d" % (i + 1))
+                    op = self._make_op(conv, bn, cur, ch, cw, relu=True)
+                    pending.append(op)
+                    cur, ch, cw = op.out_id, op.Ho, op.Wo
+                if blk.downsample is not None:
+                    dop = self._make_op(blk.downsample[0], blk.downsample[1], x_id, h, w, relu=False, signed=True)
+                    res_id, res_signed = dop.out_id, True
+                    pending.insert(len(pending) - 1, dop)
+                last = pending[-1]
+                last.res_id, last.res_signed = res_id, res_signed
+                self.ops += pending
+                x_id, h, w = last.out_id, last.Ho, last.Wo
+        for op in self.ops:
+            max_out = max(max_out, op.M * op.Cout)
+        self.final_id, self.final_hw, self.final_c = x_id, h * w, self.act[x_id].shape[3]
+        self.f32_scratch = torch.empty(max_out, dtype=torch.float32, device=dev)
+        self.act_scales = torch.ones(len(self.act), dtype=torch.float32, device=dev)
+        self.absmax_tmp = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pooled = torch.empty((N, self.final_c), dtype=torch.float32, device=dev)
+        self.logits = torch.empty((N, net.fc.out_features), dtype=torch.float32, device=dev)
+        self.calibrated = False
+
+    def _make_op(self, conv, bn, in_id, h, w, relu, signed=False):
+        op = _ConvOp()
+        op.conv, op.bn, op.in_id, op.relu, op.signed = conv, bn, in_id, relu, signed
+        op.Cin, op.Cout = conv.in_channels, conv.out_channels
+        op.k, op.stride, op.pad = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        op.H, op.W = h, w
+        op.Ho = (h + 2 * op.pad - op.k) // op.stride + 1
+        op.Wo = (w + 2 * op.pad - op.k) // op.stride + 1
+        op.M = self.N * op.Ho * op.Wo
+        op.out_id = self._new_act((self.N, op.Ho, op.Wo, op.Cout), signed)
+        op.res_id, op.res_signed = -1, False
+        op.handle, op.w16 = None, None
+        return op
+
+    # ------------------------------------------------------------------------------------------
+    def refresh_weights(self):
+        """Re-derives packed codes, GEMM-ready matrices, folded BN and conv handles from the
+        module tree's CURRENT fp32 parameters (content-derived, SURVEY.md H4 option b)."""
+        lib, dev = self.lib, self.device
+        with torch.cuda.device(dev), torch.no_grad():
+            stream = L.current_stream(dev)
+            ws = [op.conv.weight.detach().reshape(op.Cout, -1).contiguous() for op in self.ops]
+            metas = classify_weights(ws, stream)
+            for op, w2d, (bit, z, s, bits_host) in zip(self.ops, ws, metas):
+                op.packed = encode_weight(w2d, bit, z, s, bits_host, stream)
+                op.bits_host = bits_host
+                w16 = 1 if int(bits_host.max()) > 8 else 0
+                desc = L.ConvDesc(self.N, op.H, op.W, op.Cin, op.Cout, op.k, op.k, op.stride, op.pad,
+                                  w16, self.impl, self.a_mode)
+                rows = lib.slq_gemm_weight_rows(ctypes.byref(desc))
+                op.wg = torch.empty((rows, op.k * op.k * op.Cin), dtype=torch.uint8, device=dev)
+                L.check(lib.slq_build_gemm_weights(ctypes.byref(desc), op.packed.blob.data_ptr(),
+                                                   op.packed.offsets.data_ptr(), op.packed.bits.data_ptr(),
+                                                   op.wg.data_ptr(), stream))
+                if op.handle is not None:
+                    lib.slq_conv_destroy(op.handle)
+                    op.handle = None
+                h = ctypes.c_void_p()
+                L.check(lib.slq_conv_create(ctypes.byref(desc), self.act[op.in_id].data_ptr(),
+                                            op.wg.data_ptr(), ctypes.byref(h)))
+                op.handle, op.w16, op.desc = h, w16, desc
+                a, b = self._fold_bn(op.bn)
+                op.wscale = (s * a).contiguous()
+                op.zf = z.to(torch.float32)
+                op.bias = b.contiguous()
+                op.epi = {}
+            self.stem_w = self.net.conv1.weight.detach().contiguous()
+            self.stem_a, self.stem_b = self._fold_bn(self.net.bn1)
+            self.fc_w = self.net.fc.weight.detach().contiguous()
+            self.fc_b = self.net.fc.bias.detach().contiguous()
+        self.calibrated = False
+
+    @staticmethod
+    def _fold_bn(bn):
+        a = (bn.weight.detach() / torch.sqrt(bn.running_var.detach() + bn.eps)).to(torch.float32)
+        b = (bn.bias.detach() - bn.running_mean.detach() * a).to(torch.float32)
+        return a.contiguous(), b.contiguous()
+
+    def _epilogue(self, op, mode, out_ptr, out_S=None):
+        key = (mode, out_ptr)
+        e = op.epi.get(key)
+        if e is None:
+            res = self.act[op.res_id].data_ptr() if op.res_id >= 0 else None
+            e = L.Epilogue(op.wscale.data_ptr(), op.zf.data_ptr(), op.bias.data_ptr(),
+                           self.act_scales.data_ptr(), op.in_id, op.out_id, op.res_id, res,
+                           1 if op.res_signed else 0, out_ptr, out_S, mode, 1 if op.relu else 0)
+            op.epi[key] = e
+        return e
+
+    # ------------------------------------------------------------------------------------------
+    def _check_x(self, x):
+        if tuple(x.shape) != (self.N, 3, self.H, self.W) or x.dtype != torch.float32 or not x.is_cuda:
+            raise ValueError("engine compiled for fp32 CUDA input %s, got %s %s" %
+                             ((self.N, 3, self.H, self.W), tuple(x.shape), x.dtype))
+        return x.contiguous()
+
+    def calibrate(self, x):
+        """One pass with fp32 layer outputs: every activation tensor's static scale becomes
+        absmax/255 (u8) or absmax/127 (s8) of this batch; tensors are then re-quantised so that
+        the pass also leaves the same bytes in HBM that forward(x) will produce."""
+        lib = self.lib
+        x = self._check_x(x)
+        with torch.cuda.device(self.device):
+            st = L.current_stream(self.device)
+            sc, tmp, f32 = self.act_scales.data_ptr(), self.absmax_tmp.data_ptr(), self.f32_scratch
+            n0 = self.act[0].numel()
+            L.check(lib.slq_stem_forward(x.data_ptr(), self.N, self.H, self.W, self.stem_w.data_ptr(),
+                                         self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
+                                         self.stem_scratch.data_ptr(), f32.data_ptr(), L.OUT_F32, st))
+            L.check(lib.slq_absmax_scale(f32.data_ptr(), n0, sc, 0, 255, tmp, st))
+            L.check(lib.slq_quantize_act(f32.data_ptr(), n0, sc, 0, 0, self.act[0].data_ptr(), st))
+            for op in self.ops:
+                n = op.M * op.Cout
+                L.check(lib.slq_conv_launch(op.handle, ctypes.byref(self._epilogue(op, L.OUT_F32, f32.data_ptr())), st))
+                L.check(lib.slq_absmax_scale(f32.data_ptr(), n, sc, op.out_id, 127 if op.signed else 255, tmp, st))
+                L.check(lib.slq_quantize_act(f32.data_ptr(), n, sc, op.out_id, 1 if op.signed else 0,
+                                             self.act[op.out_id].data_ptr(), st))
+        self.calibrated = True
+
+    def forward(self, x):
+        """Static-scale inference pass: stem -> conv launches -> tail.  Returns the engine's
+        logits buffer [N, num_classes] (overwritten by the next call)."""
+        if not self.calibrated:
+            raise RuntimeError("engine is not calibrated (call calibrate(x) after refresh_weights())")
+        x = self._check_x(x)
+        self.launch_all(x.data_ptr(), L.current_stream(self.device))
+        return self.logits
+
+    def launch_all(self, x_ptr, st):
+        lib = self.lib
+        sc = self.act_scales.data_ptr()
+        L.check(lib.slq_stem_forward(x_ptr, self.N, self.H, self.W, self.stem_w.data_ptr(),
+                                     self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
+                                     self.stem_scratch.data_ptr(), self.act[0].data_ptr(), L.OUT_U8, st))
+        for op in self.ops:
+            mode = L.OUT_S8 if op.signed else L.OUT_U8
+            e = self._epilogue(op, mode, self.act[op.out_id].data_ptr())
+            L.check(lib.slq_conv_launch(op.handle, ctypes.byref(e), st))
+        L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
+                                     sc, self.final_id, self.fc_w.data_ptr(), self.fc_b.data_ptr(),
+                                     self.logits.shape[1], self.pooled.data_ptr(), self.logits.data_ptr(), st))
+        self.kernel_launches = 2 + len(self.ops) + 2
+
+    # ------------------------------------------------------------------------------------------
+    def capture_graph(self, x_static):
+        """Captures one forward into a CUDA graph reading from x_static (fp32 NCHW device buffer)."""
+        x_static = self._check_x(x_static)
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            self.launch_all(x_static.data_ptr(), s.cuda_stream)  # warm-up outside capture
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        with torch.cuda.graph(g, stream=s):
+            self.launch_all(x_static.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        self.graph, self.graph_x = g, x_static
+        return g
+
+    def weight_bytes(self):
+        return sum(op.packed.nbytes for op in self.ops)
+
+    def describe(self):
+        rows = []
+        for op in self.ops:
+            bits, counts = np.unique(op.bits_host, return_counts=True)
+            rows.append(dict(Cin=op.Cin, Cout=op.Cout, k=op.k, stride=op.stride, H=op.H, M=op.M, w16=op.w16,
+                             bits={int(b): int(c) for b, c in zip(bits, counts)}))
+        return rows
+
+    def __del__(self):
+        try:
+            for op in getattr(self, "ops", []):
+                if getattr(op, "handle", None) is not None:
+                    self.lib.slq_conv_destroy(op.handle)
+                    op.handle = None
+        except Exception:
+            pass

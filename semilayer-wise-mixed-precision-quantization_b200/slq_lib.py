@@ -1,0 +1,97 @@
+"""slq_lib.py -- ctypes binding of libslq_b200.so (include/slq.h).
+
+This is the ONLY way the Python host reaches the CUDA kernels: plain pointers and sizes across a
+C ABI; torch only provides device memory (``tensor.data_ptr()``) and the current CUDA stream.
+There is no CPU fallback: if the library cannot be loaded, every entry point raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libslq_b200.so")
+
+SLQ_OK, SLQ_ERR_INVALID, SLQ_ERR_CUDA, SLQ_ERR_ZERO_RANGE, SLQ_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
+ROW_OK, ROW_ZERO_RANGE, ROW_CODE_RANGE = 0, 1, 2
+DIV_TRUE, DIV_RECIP = 0, 1
+IMPL_UMMA, IMPL_SIMT = 0, 1
+A_AUTO, A_IM2COL, A_TILED = 0, 1, 2
+OUT_U8, OUT_F32, OUT_ACC, OUT_S8 = 0, 1, 2, 3
+
+_i32, _i64, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [(n, _i32) for n in
+                ("N", "H", "W", "Cin", "Cout", "kh", "kw", "stride", "pad", "w16", "impl", "a_mode")]
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [("wscale", _vp), ("zf", _vp), ("bias", _vp), ("act_scales", _vp),
+                ("in_id", _i32), ("out_id", _i32), ("res_id", _i32),
+                ("res", _vp), ("res_signed", _i32),
+                ("out", _vp), ("out_S", _vp), ("out_mode", _i32), ("relu", _i32)]
+
+
+# name -> (restype, argtypes); mirrors include/slq.h one to one (tests check the export list)
+SIGNATURES = {
+    "slq_last_error": (ctypes.c_char_p, []),
+    "slq_abi_version": (ctypes.c_int, []),
+    "slq_device_info": (ctypes.c_int, [_vp, _vp, _vp]),
+    "slq_packed_row_bytes": (_i64, [_i64, _i32]),
+    "slq_quantize_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "slq_quantize_rows_host": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "slq_classify_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "slq_encode_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "slq_gemm_weight_rows": (_i64, [ctypes.POINTER(ConvDesc)]),
+    "slq_build_gemm_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "slq_conv_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, ctypes.POINTER(_vp)]),
+    "slq_conv_destroy": (None, [_vp]),
+    "slq_conv_launch": (ctypes.c_int, [_vp, ctypes.POINTER(Epilogue), _vp]),
+    "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "slq_tail_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
+    "slq_absmax_scale": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+    "slq_quantize_act": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+class SlqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libslq_b200: error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Loads libslq_b200.so (building is __graft_entry__.build()'s / slq_build.build()'s job)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libslq_b200.so is missing (%s). Build it with `python slq_build.py`; this package "
+                "has no CPU or eager-PyTorch fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        if L.slq_abi_version() != 1:
+            raise RuntimeError("libslq_b200.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != SLQ_OK:
+        msg = lib().slq_last_error()
+        raise SlqError(rc, msg.decode() if msg else "")
+
+
+def ptr(t):
+    """Device/host address of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream(device=None):
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
