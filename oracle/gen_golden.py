@@ -79,7 +79,7 @@ def gen_quant():
             out["q%d" % n] = q
             out["z%d" % n] = np.int32(z)
             out["s%d" % n] = np.float32(s32)
-            out["c%d" % n] = codes.astype(np.uint8) if bit <= 8 else codes
+            out["c%d" % n] = codes.astype(np.int32)  # may exceed 2^bit-1 on tie rows
             n += 1
     # progressive 8 -> 6 -> 4 on one row through channel_wise_quantizationperchan
     t = net.layer2[0].conv2.weight.data[:4].clone()
