@@ -150,6 +150,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16, help="images per step of the CPU reference arm")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-agree", action="store_true", help="skip the fp32 agreement check (torch kernels)")
     ap.add_argument("--simt", action="store_true", help="run the dp4a checker kernels instead (debug)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -209,6 +210,8 @@ def main():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     agree = rel = None
     try:
+        if args.no_agree:
+            raise RuntimeError("skipped")
         import slq_oracle as so
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False

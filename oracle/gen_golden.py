@@ -181,6 +181,9 @@ def gen_sweep():
         ds.append([li, bi, lnum[i], cnum[i], dl[0][i], dl[1][i], dl[2][i], dl[3][i]])
         rows.append([li, bi, lnum[i], cnum[i], 8, 0, 32, i + 1])
     minus, plus = functions.make_divide_minusplusmodels(rows, ds, 4)
+    in_rows = np.array(rows, np.int64)
+    in_dl8 = np.array([d[4] for d in ds], np.float64)
+    minus_rows, plus_rows = np.array(minus, np.int64), np.array(plus, np.int64)
     semilayers, orders = functions.make_semilayers_resnet18(net2, "cpu", orig, minus, plus)
     orders_unsorted = [list(o) for o in orders]
     flat = functions.make_quantizedlists(semilayers, orders)
@@ -191,6 +194,8 @@ def gen_sweep():
         sorted_index=np.array([o[0] for o in orders], np.int32),
         semilayer_sizes=np.array([len(s) for s in semilayers], np.int32),
         flat=np.array(flat, np.int64),
+        in_rows=in_rows, in_dl8=in_dl8, minus_rows=minus_rows, plus_rows=plus_rows,
+        net2_row_after=net2.layer1[0].conv1.weight.data[int(minus_rows[0][3])].reshape(-1).numpy(),
         minus_len=np.int32(len(minus) - 1), plus_len=np.int32(len(plus) - 1))
     print("sweep: orders", len(orders_unsorted), "flat", len(flat), "loss0", loss0)
     rh.unload_reference()

@@ -1,0 +1,129 @@
+"""CPU suite for the host side that mirrors the reference's functions.py / resnet.py interface:
+semilayer split, sweep, ranked list, evaluation and the module-tree contract, checked against
+fixtures produced by the UNMODIFIED reference (oracle/gen_golden.py).  The CUDA entry points are
+replaced by the oracle here (tests/cpu_standins.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cpu_standins
+from helpers import GOLD
+
+
+@pytest.fixture(scope="module")
+def sw():
+    return np.load(os.path.join(GOLD, "sweep_resnet18.npz"))
+
+
+def _rows(a):
+    return [[int(v) for v in r] for r in a]
+
+
+def test_split_matches_reference(sw, capsys):
+    import functions
+    rows = _rows(sw["in_rows"])
+    ds = [[r[0], r[1], r[2], r[3], float(d)] for r, d in zip(rows, sw["in_dl8"])]
+    minus, plus = functions.make_divide_minusplusmodels(rows, ds, 4)
+    assert minus == _rows(sw["minus_rows"]) and plus == _rows(sw["plus_rows"])
+    assert "function debug:number of total channels= 3840" in capsys.readouterr().out
+    # zero counts as minus; flags run 0,-1,-2.. / 1,2,3.. per layer
+    assert minus[0][5] == 0 and plus[0][5] == 1
+    assert min(r[5] for r in minus) == -15 and max(r[5] for r in plus) == 16
+
+
+def test_sweep_and_ranked_list_match_reference(sw, monkeypatch):
+    """functions.make_semilayers_resnet18 + make_quantizedlists on the tiny synthetic loader the
+    golden run used (2 batches of 4 images, 64x64): same semilayers, same sensitivities (KL/param),
+    same ranked channel list; candidate 0 mutates the caller's net (reference quirk Q3)."""
+    import functions
+    import imagenet
+    import resnet
+    cpu_standins.install(monkeypatch)
+    loader = imagenet.synthetic_loader(2, 4, 64, seed=1)
+    monkeypatch.setattr(imagenet, "val_loader", loader)
+    torch.manual_seed(0)
+    sd = resnet.resnet18(num_classes=1000).state_dict()
+    monkeypatch.setattr(resnet, "load_state_dict_from_url", lambda url, progress=True: sd)
+    net2 = resnet.resnet18(num_classes=1000, pretrained="imagenet")
+    preacc, loss0, orig = functions.evaluate_acc_loss_softmax(net2, "cpu", loader)
+    assert abs(loss0 - float(sw["loss0"])) < 1e-5 and preacc == float(sw["preacc"])
+    minus, plus = _rows(sw["minus_rows"]), _rows(sw["plus_rows"])
+    semilayers, orders = functions.make_semilayers_resnet18(net2, "cpu", orig, minus, plus)
+    assert minus[-1] == [0, 0, 100, 0, 0, 0, 0, 0] and plus[-1][2] == 100  # caller's lists mutated
+    assert [len(s) for s in semilayers] == sw["semilayer_sizes"].tolist()
+    gold = sw["orders"]
+    assert [o[0] for o in orders] == gold[:, 0].astype(int).tolist()
+    got = np.array([o[1] for o in orders])
+    assert np.allclose(got, gold[:, 1], rtol=2e-3, atol=1e-12), np.abs(got / gold[:, 1] - 1).max()
+    c0 = int(sw["minus_rows"][0][3])
+    assert np.array_equal(net2.layer1[0].conv1.weight.data[c0].reshape(-1).numpy(), sw["net2_row_after"])
+    flat = functions.make_quantizedlists(semilayers, orders)
+    assert [o[0] for o in orders] == sw["sorted_index"].tolist()
+    assert np.array_equal(np.array(flat, np.int64), sw["flat"])
+
+
+def test_kldiv_and_evaluate_conventions():
+    import functions
+    p = [torch.softmax(torch.randn(4, 10, generator=torch.Generator().manual_seed(i)), 1) for i in range(3)]
+    q = [torch.softmax(torch.randn(4, 10, generator=torch.Generator().manual_seed(9 + i)), 1) for i in range(3)]
+    want = sum((a[m] * (a[m] / b[m]).log()).sum() for a, b in zip(p, q) for m in range(4)) / 12
+    assert abs(functions.KLdiv(p, q) - want.item()) < 1e-6
+    assert functions.KLdiv(p, p) == 0.0
+
+
+def test_quantizer_entry_points_inplace_contract(monkeypatch):
+    import functions
+    cpu_standins.install(monkeypatch)
+    import slq_oracle as so
+    t = torch.randn(4, 3, 3, 3, generator=torch.Generator().manual_seed(0))
+    before = t.clone()
+    out = functions.channel_wise_quantizationperchan(t, 4, 2)
+    assert out is t
+    assert torch.equal(t[0], before[0]) and not torch.equal(t[2], before[2])
+    q, _, _, _, _ = so.quantize_row(before[2].reshape(-1).numpy(), 4)
+    assert np.array_equal(t[2].reshape(-1).numpy(), q)
+    fresh = functions.quantize_wgt(before[1], 8)
+    assert fresh is not before[1] and fresh.shape == before[1].shape
+    with pytest.raises(ZeroDivisionError):
+        so.quantize_row(np.zeros(8, np.float32), 8)
+
+
+def test_module_tree_contract():
+    """Attribute names, state_dict keys and parameter shapes the mains index."""
+    import resnet
+    import torchvision
+    for arch, counts in (("resnet18", 16), ("resnet34", 32), ("resnet50", 48)):
+        net = getattr(resnet, arch)(num_classes=1000)
+        tv = getattr(torchvision.models, arch)(weights=None)
+        assert list(net.state_dict().keys()) == list(tv.state_dict().keys())
+        for k, v in tv.state_dict().items():
+            assert net.state_dict()[k].shape == v.shape
+        blocks = [b for s in (net.layer1, net.layer2, net.layer3, net.layer4) for b in s]
+        n = sum(1 for b in blocks for c in ("conv1", "conv2", "conv3") if hasattr(b, c))
+        assert n == counts
+        assert net.layers[0] is net.layer1
+        w = net.layer2[0].conv2.weight
+        assert w[3].data.numel() == w.shape[1] * 9  # resnet50_main.py:132 reads this
+    net = resnet.resnet50(num_classes=1000)
+    assert net.layer1[0].conv2.stride == (1, 1) and net.layer2[0].conv2.stride == (2, 2)  # v1.5
+    assert net.layer2[0].conv1.stride == (1, 1) and net.layer2[0].downsample[0].stride == (2, 2)
+    net.load_state_dict(net.state_dict())
+    assert net._slq_dirty
+
+
+def test_engine_invalidation_hooks(monkeypatch):
+    import functions
+    import resnet
+    cpu_standins.install(monkeypatch)
+    net = resnet.resnet18(num_classes=10).eval()
+    net._slq_dirty = False
+    e0 = resnet.WEIGHT_EPOCH[0]
+    net.layer1[0].conv1.weight.data = functions.channel_wise_quantizationperchan(net.layer1[0].conv1.weight.data, 8, 0)
+    assert resnet.WEIGHT_EPOCH[0] == e0 + 1
+    net.eval()
+    assert net._slq_dirty
+    net._slq_dirty = False
+    net.to("cpu")
+    assert net._slq_dirty
