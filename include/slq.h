@@ -46,7 +46,7 @@ extern "C" {
 
 /* fp32 divide flavour of functions.py:41 `tensor/scale` */
 #define SLQ_DIV_TRUE 0  /* IEEE fp32 divide: what ATen does for CPU tensors */
-#define SLQ_DIV_RECIP 1 /* multiply by the fp32 reciprocal: ATen CUDA div by a CPU scalar */
+#define SLQ_DIV_RECIP 1 /* multiply by float32(1.0 / scale64): ATen CUDA div by a CPU scalar */
 
 SLQ_API const char *slq_last_error(void);
 SLQ_API int slq_abi_version(void);
@@ -177,6 +177,23 @@ SLQ_API int slq_conv_launch(slq_conv *c, const slq_epilogue *e, void *stream);
 SLQ_API int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W, const float *w,
                      const float *bn_a, const float *bn_b, const float *act_scales, int32_t out_id,
                      float *scratch, void *out, int32_t out_mode, void *stream);
+
+/* The same stem on the tensor cores (the product path; slq_stem_forward above is the exact-fp32
+ * CUDA-core version kept as on-device checker and for W > 256).  Operands pass through tcgen05 as
+ * fp16 with fp32 accumulation -- these weights are NOT quantised (the reference keeps them fp32).
+ * `workspace` (slq_stem_workspace_bytes, 256-byte aligned, caller-owned) holds the row-expanded
+ * fp16 image, the pre-pool u8 activations and the fp16 weight matrix.
+ * out: u8 NHWC [N,Hp,Wp,64] (SLQ_OUT_U8, scale act_scales[out_id]) or fp32 (SLQ_OUT_F32; then
+ * f32_scratch must hold N*Hc*Wc*64 floats).                                                      */
+typedef struct slq_stem slq_stem;
+SLQ_API int64_t slq_stem_workspace_bytes(int32_t N, int32_t H, int32_t W);
+SLQ_API int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace, slq_stem **out);
+SLQ_API void slq_stem_destroy(slq_stem *s);
+/* w: fp32 [64,3,7,7] device pointer (resnet.py:143 conv1.weight) */
+SLQ_API int slq_stem_set_weights(slq_stem *s, const float *w, void *stream);
+SLQ_API int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, const float *bn_b,
+                            const float *act_scales, int32_t out_id, void *out, int32_t out_mode,
+                            float *f32_scratch, void *stream);
 
 /* Tail: resnet.py:216-218  adaptive_avg_pool2d((1,1)) + flatten + fc (fp32 weights + bias).
  * x u8 NHWC [N, HW, C] -> logits fp32 [N, O]; pooled is scratch [N, C] fp32.                     */

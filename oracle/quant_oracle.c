@@ -23,7 +23,7 @@
 #define SLQ_ORACLE_CODE_RANGE 2 /* a code fell outside [0, 2^bit-1]; value clamped in codes_out */
 
 /* div_mode 0: true IEEE fp32 divide      (ATen CPU path of `tensor/scale`, functions.py:41)
- * div_mode 1: multiply by fp32 reciprocal (ATen CUDA div_true kernel with a CPU-scalar divisor) */
+ * div_mode 1: multiply by float32(1.0/scale64) (ATen CUDA div_true kernel with a CPU-scalar divisor) */
 int slq_oracle_quantize_row(const float *w, int64_t K, int bit, int div_mode,
                             float *q_out,      /* K  fake-quantised fp32 values (may alias w)   */
                             int32_t *codes_out, /* K  stored codes u = k - z (may be NULL)        */
@@ -46,7 +46,9 @@ int slq_oracle_quantize_row(const float *w, int64_t K, int bit, int div_mode,
     /* A.4  the python float meets an fp32 tensor: demoted with round-to-nearest-even */
     float s32 = (float)scale;
     float zf = (float)zd;
-    volatile float inv = 1.0f / s32;
+    /* ATen CUDA div by a CPU scalar: inv_b = float(1.0 / double(scalar)), computed on the host in
+     * double from the python float (measured on B200, torch 2.11: tools/diag_div.py, 0 of 21M off) */
+    volatile float inv = (float)(1.0 / scale);
     int status = SLQ_ORACLE_OK;
     int32_t maxcode = (int32_t)((1LL << bit) - 1);
     for (int64_t i = 0; i < K; ++i) {

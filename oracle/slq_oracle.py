@@ -183,26 +183,61 @@ def conv_acc(x_u8, codes_ohwi, stride, pad):
     return A @ B.T, A.sum(1), Ho, Wo
 
 
-def epilogue(acc, S, zf, wscale, bias, s_in, res_u8=None, s_res=None, relu=True):
-    """fp32 epilogue exactly as csrc/epilogue.cuh computes it (separately rounded mul/add):
-       v = f32(acc) + zf*f32(S);  y = (v*(wscale*s_in)) + bias;  y += f32(res)*s_res;  relu."""
+def fma32(a, b, c):
+    """Exactly-rounded float32 fused multiply-add on numpy arrays (what __fmaf_rn computes).
+    a*b is exact in float64; the float64 sum is then corrected for double rounding with the exact
+    TwoSum error term, so the result equals round_to_float32(a*b + c) computed exactly."""
+    a64, b64, c64 = (np.asarray(v, np.float32).astype(np.float64) for v in (a, b, c))
+    p = a64 * b64
+    s = p + c64
+    bb = s - p
+    err = (p - (s - bb)) + (c64 - bb)          # p + c == s + err exactly
+    r = s.astype(np.float32)
+    rd = r.astype(np.float64)
+    up = np.nextafter(r, np.float32(np.inf))
+    dn = np.nextafter(r, np.float32(-np.inf))
+    other = np.where(s > rd, up, dn)
+    od = other.astype(np.float64)
+    tie = (s == (rd + od) / 2) & (s != rd)
+    toward = np.sign(err) == np.sign(od - rd)
+    return np.where(tie & (err != 0) & toward, other, r).astype(np.float32)
+
+
+def epilogue(acc, S, zf, wscale, bias, s_in, res_u8=None, s_res=None, relu=True, acc_hi=None,
+             res_signed=False):
+    """fp32 epilogue exactly as csrc/epilogue.cuh computes it (fma = one rounding):
+         wsc = wscale*s_in ; zw = zf*wsc
+         accf = f32(acc) [two limbs: fma(f32(hi), 256, f32(lo))]
+         y = fma(accf, wsc, fma(f32(S), zw, bias)) ; y = fma(f32(res), s_res, y)
+       Returns the fp32 output (ReLU applied when relu)."""
     f = np.float32
-    accf = acc.astype(np.float32)
-    Sf = S.astype(np.float32)[:, None]
-    v = (accf + (zf.astype(f)[None, :] * Sf).astype(f)).astype(f)
-    sc = (wscale.astype(f) * f(s_in)).astype(f)
-    y = ((v * sc[None, :]).astype(f) + bias.astype(f)[None, :]).astype(f)
+    wsc = (wscale.astype(f) * f(s_in)).astype(f)
+    zw = (zf.astype(f) * wsc).astype(f)
+    accf = acc.astype(f)
+    if acc_hi is not None:
+        accf = fma32(acc_hi.astype(f), f(256.0), accf)
+    c2 = fma32(S.astype(f)[:, None], zw[None, :], bias.astype(f)[None, :])
+    y = fma32(accf, wsc[None, :], c2)
     if res_u8 is not None:
-        y = (y + (res_u8.astype(f) * f(s_res)).astype(f)).astype(f)
+        r = res_u8.view(np.int8).astype(f) if res_signed else res_u8.astype(f)
+        y = fma32(r, f(s_res), y)
     if relu:
         y = np.maximum(y, f(0))
     return y
 
 
 def requant_u8(y, s_out):
+    """cvt.rni.sat.u8.f32(y * (1/s_out))"""
     inv = np.float32(1.0) / np.float32(s_out)
-    q = np.rint((y * inv).astype(np.float32))
-    return np.clip(q, 0, 255).astype(np.uint8)
+    q = np.rint((np.asarray(y, np.float32) * inv).astype(np.float32))
+    return np.clip(np.nan_to_num(q, nan=0.0), 0, 255).astype(np.uint8)
+
+
+def requant_s8(y, s_out):
+    """cvt.rni.sat.s8.f32(y * (1/s_out)), returned as the raw byte"""
+    inv = np.float32(1.0) / np.float32(s_out)
+    q = np.rint((np.asarray(y, np.float32) * inv).astype(np.float32))
+    return np.clip(np.nan_to_num(q, nan=0.0), -128, 127).astype(np.int8).view(np.uint8)
 
 
 def act_scale_from_absmax(amax):

@@ -47,6 +47,10 @@ int validate_desc(const slq_conv_desc *d);  // SLQ_OK or error (message set)
 int launch_conv_simt(const ConvGeom &g, const uint8_t *in, const uint8_t *wg, const EpiDev &e,
                      cudaStream_t st);
 
+// fp32 3x3 s2 max-pool of the stem (+ optional u8 quantisation), layers.cu
+int launch_stem_pool(const float *y, int N, int Hc, int Wc, int Hp, int Wp, const float *act_scales,
+                     int out_id, void *out, int out_mode, cudaStream_t st);
+
 }  // namespace slq
 
 struct slq_conv {
@@ -58,6 +62,10 @@ struct slq_conv {
   int swizzle;      // 64 or 128: bytes of K per pipeline stage == TMA/UMMA swizzle span
   CUtensorMap tmA;  // activations
   CUtensorMap tmB;  // GEMM-ready weights
+  CUtensorMap tmO;  // [M, Cout] output (TMA store), encoded for out_ptr at launch
+  CUtensorMap tmR;  // [M, Cout] residual (TMA load), encoded for res_ptr at launch
+  const void *out_ptr;
+  const void *res_ptr;
   int num_ctas;
   int smem_bytes;
 };

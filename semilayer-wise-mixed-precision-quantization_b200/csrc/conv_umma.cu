@@ -10,188 +10,95 @@
 //   One extra "ones" B row per tile makes the tensor core also produce the window sum
 //   S[m] = sum_k A[m, k] that the zero-point correction z[oc]*S[m] needs.
 //
-// Persistent, warp-specialised CTA (256 threads, 1 CTA/SM):
-//   warp 0   TMA producer           (one lane)   smem ring of kStages x {A 128xSWZ, B (bn+16)xSWZ}
-//   warp 1   tcgen05.mma issuer     (one lane)   accumulators double-buffered in TMEM (2 x 256 cols)
-//   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld -> de-quantise + folded BN + residual + ReLU -> u8 NHWC store
+// Persistent, warp-specialised CTA (384 threads, 1 CTA/SM):
+//   warp 0     TMA producer (A, B)    one lane; smem ring of kStages x {A 128xSWZ, B (bn+16)xSWZ}
+//   warp 1     tcgen05.mma issuer     one lane; accumulators double-buffered in TMEM (2 x 256 cols)
+//   warp 2     TMEM allocator
+//   warp 3     residual producer      one lane; TMA-loads the identity tile of the block
+//   warps 4-7  epilogue group 0  \  tile i -> group i&1: tcgen05.ld -> dequant + folded BN + residual
+//   warps 8-11 epilogue group 1  /  + ReLU -> u8 into a swizzled smem tile -> ONE TMA store per tile
+// so the global traffic of the epilogue is fully coalesced 128-byte lines in both directions.
 #include <algorithm>
 #include <new>
 
 #include "conv_common.cuh"
+#include "umma_ptx.cuh"
 
 namespace slq {
 
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-  return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 1.9 GHz
-      printf("slq conv_umma: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x,
-             threadIdx.x, bar, parity);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async_smem() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0,
-                                            int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar,
-                                                   int c, int w, int h, int n, uint16_t off_w,
-                                                   uint16_t off_h) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem], 8-bit integer operands, single CTA
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
-  uint32_t v;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
-  return v;
-}
-__device__ __forceinline__ void tmem_ld_wait() {
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major shared-memory matrix descriptor for a tile whose rows are SWZ bytes long and stored with
-// the SWZ-byte TMA/UMMA swizzle (8-row groups of 8*SWZ bytes, tile base aligned to 1024 B).
-template <int SWZ>
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-  constexpr uint64_t kLayout = (SWZ == 128) ? 2 : 4;  // SWIZZLE_128B / SWIZZLE_64B
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);   // start address  [0,14)
-  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)((8 * SWZ) >> 4) << 32;      // stride byte offset: next 8-row group
-  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
-  d |= kLayout << 61;
-  return d;
-}
+constexpr int kThreads = 384;
+constexpr int kOutTileBytes = kTileM * 128;  // u8 output / residual staging tile (128 rows x <=128 B)
 
 template <int SWZ>
 struct Cfg {
-  static constexpr int kStages = (SWZ == 128) ? 6 : 8;
+  static constexpr int kStages = (SWZ == 128) ? 4 : 6;
   static constexpr int kABytes = kTileM * SWZ;
   static constexpr int kBRows = 128 + 16;  // bn_cols (<=128) + 16 rows for the ones-row group
   static constexpr int kBBytes = kBRows * SWZ;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kParamBytes = 128 * 16;  // float4 {wscale*s_in, zf, bias, -} per channel
-  static constexpr int kBarBytes = 256;
-  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kParamBytes + kBarBytes;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kOutOff = kPipeBytes;                      // 2 output staging tiles
+  static constexpr int kResOff = kOutOff + 2 * kOutTileBytes;     // 2 residual tiles
+  static constexpr int kPrmOff = kResOff + 2 * kOutTileBytes;     // 2 x 128 ChanParam
+  static constexpr int kBarOff = kPrmOff + 2 * 128 * 16;
+  static constexpr int kSmemBytes = 1024 + kBarOff + 256;
   static_assert(kStageBytes % 1024 == 0, "stage must keep 1024B alignment");
+  static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
 };
 
 struct KernelArgs {
   ConvGeom g;
   EpiDev e;
   int a_im2col;
-  int num_kb;         // K blocks per tile = kh*kw*Cin / SWZ
-  int chunks_per_tap; // Cin / SWZ
+  int num_kb;          // K blocks per tile = kh*kw*Cin / SWZ
+  int chunks_per_tap;  // Cin / SWZ
+  int tma_out;         // 1: u8/s8 output through the smem tile + TMA store
   long long m_tiles;
 };
 
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
 constexpr int kTmemCols = 512;
 
+// byte offset of 16-byte chunk c of row r inside a staging tile whose rows are bn_ch (64|128) bytes,
+// stored with the TMA swizzle of that width (so that thread-per-row accesses are conflict-free)
+__device__ __forceinline__ uint32_t stage_off(int r, int c, int bn_ch) {
+  return bn_ch == 128 ? (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))
+                      : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+}
+
 template <int SWZ, bool W16>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                  const KernelArgs a) {
   using C = Cfg<SWZ>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  float4 *prm = reinterpret_cast<float4 *>(smem + C::kStages * C::kStageBytes);
-  const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes + C::kParamBytes;
-  // barrier slots (8 bytes each): full[kStages] | empty[kStages] | tmem_full[2] | tmem_empty[2] | tmem ptr
+  const uint32_t bar_base = smem_base + C::kBarOff;
+  // barrier slots (8 bytes each)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + b); };
   auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 2 + b); };
-  volatile uint32_t *tmem_slot =
-      reinterpret_cast<volatile uint32_t *>(smem + C::kStages * C::kStageBytes + C::kParamBytes + 8 * (2 * C::kStages + 4));
+  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 4 + b); };
+  auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 6 + b); };
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::kBarOff + 8 * (2 * C::kStages + 8));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom &g = a.g;
+  const EpiDev &e = a.e;
   const int bn_cols = g.bn_cols;
   const int umma_n = bn_cols + 16;
   const long long total_tiles = a.m_tiles * g.n_tiles;
+  const bool has_res = e.res != nullptr;
 
   // ---- one-time setup -----------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (a.tma_out) prefetch_tmap(&tmO);
+    if (has_res) prefetch_tmap(&tmR);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::kStages; ++s) {
@@ -201,6 +108,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), 128);
+      mbar_init(rfull_bar(b), 1);
+      mbar_init(rempty_bar(b), 128);
     }
     fence_barrier_init();
   }
@@ -291,41 +200,63 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
       }
     }
+  } else if (warp == 3) {
+    // ================================ residual producer =======================================
+    if (lane == 0 && has_res) {
+      const uint32_t res_bytes = (uint32_t)(kTileM * g.bn_ch);
+      long long it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int buf = (int)(it & 1);
+        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+        mbar_wait(rempty_bar(buf), ph ^ 1);
+        mbar_expect_tx(rfull_bar(buf), res_bytes);
+        tma_load_2d(smem_base + C::kResOff + buf * kOutTileBytes, &tmR, rfull_bar(buf),
+                    (int)(tile % g.n_tiles) * g.bn_ch, (int)((tile / g.n_tiles) * kTileM));
+      }
+    }
   } else if (warp >= 4) {
-    // ================================ epilogue ================================================
-    const EpiDev &e = a.e;
-    const int wq = warp & 3;  // TMEM lane quarter this warp may touch
-    const int et = threadIdx.x - 128;
-    const bool has_res = e.res != nullptr;
+    // ================================ epilogue (2 groups of 4 warps) ===========================
+    const int grp = (warp - 4) >> 2;
+    const int wq = warp & 3;                       // TMEM lane quarter this warp may touch
+    const int et = threadIdx.x - 128 - grp * 128;  // 0..127 inside the group
+    const int row = wq * 32 + lane;                // tile row == TMEM lane
+    ChanParam *prm = reinterpret_cast<ChanParam *>(smem + C::kPrmOff) + grp * 128;
+    const uint32_t stg = smem_base + C::kOutOff + grp * kOutTileBytes;
+    const uint32_t rsb = smem_base + C::kResOff + grp * kOutTileBytes;
     float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
     if (e.out_mode != SLQ_OUT_ACC) {
       s_in = e.act_scales[e.in_id];
       if (has_res) s_res = e.act_scales[e.res_id];
       if (e.out_mode != SLQ_OUT_F32) inv_out = __fdiv_rn(1.0f, e.act_scales[e.out_id]);
     }
+    const bool res_signed = e.res_signed != 0;
+    const bool sgn_out = e.out_mode == SLQ_OUT_S8;
     const int chunks = g.bn_ch / 32;
-    long long it = 0;
     int last_n_tile = -1;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    long long it = grp;
+    for (long long tile = blockIdx.x + (long long)grp * gridDim.x; tile < total_tiles;
+         tile += 2LL * gridDim.x, it += 2) {
       const long long m_tile = tile / g.n_tiles;
       const int n_tile = (int)(tile % g.n_tiles);
-      const int buf = (int)(it & 1);
-      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      // staging tile free again? (the previous TMA store of this group has read it)
+      if (a.tma_out && et == 0) tma_store_wait_read();
+      named_bar_sync(1 + grp, 128);
       if (n_tile != last_n_tile && e.out_mode != SLQ_OUT_ACC) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's readers are done
         if (et < g.bn_ch) {
           const int oc = n_tile * g.bn_ch + et;
-          float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (oc < g.Cout) p = make_float4(__fmul_rn(e.wscale[oc], s_in), e.zf[oc], e.bias[oc], 0.f);
+          ChanParam p = {0.f, 0.f, 0.f, 0.f};
+          if (oc < g.Cout) p = make_chan_param(e.wscale[oc], e.zf[oc], e.bias[oc], s_in);
           prm[et] = p;
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
         last_n_tile = n_tile;
       }
-      mbar_wait(tfull_bar(buf), acc_phase);
+      named_bar_sync(1 + grp, 128);
+      mbar_wait(tfull_bar(grp), ph);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * kAccStride;
-      const long long m = m_tile * kTileM + wq * 32 + lane;
+      if (has_res) mbar_wait(rfull_bar(grp), ph);
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + grp * kAccStride;
+      const long long m = m_tile * kTileM + row;
       const bool valid = m < g.M;
       const uint32_t S_raw = tmem_ld1(trow + bn_cols);
       tmem_ld_wait();
@@ -337,8 +268,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (W16) tmem_ld32(trow + 64 + ch * 32, hi);
         tmem_ld_wait();
         const int cb = n_tile * g.bn_ch + ch * 32;  // first output channel of this chunk
-        if (!valid || cb >= g.Cout) continue;
         if (e.out_mode == SLQ_OUT_ACC) {
+          if (!valid || cb >= g.Cout) continue;
           const long long ld = (long long)(W16 ? 2 : 1) * g.Cout;
           int4 *o = reinterpret_cast<int4 *>(reinterpret_cast<int32_t *>(e.out) + m * ld + cb);
 #pragma unroll
@@ -352,42 +283,57 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         uint32_t rw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (has_res) {
-          const uint4 *rp = reinterpret_cast<const uint4 *>(e.res + m * g.Cout + cb);
-          const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          const uint4 r0 = lds128(rsb + stage_off(row, 2 * ch, g.bn_ch));
+          const uint4 r1 = lds128(rsb + stage_off(row, 2 * ch + 1, g.bn_ch));
           rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w;
           rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
         }
-        float y[32];
+        const bool f32_out = e.out_mode == SLQ_OUT_F32;
+        const bool store_ok = valid && cb < g.Cout;
+        float4 *of = reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.out) + m * g.Cout + cb);
+        uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const float4 p = prm[ch * 32 + j];
-          float v = epi_value((int)lo[j], W16 ? (int)hi[j] : 0, W16, Sf, p.y, p.x, p.z);
-          const int rraw = (int)((rw[j >> 2] >> (8 * (j & 3))) & 255u);
-          y[j] = epi_residual_relu(v, has_res, rraw, e.res_signed != 0, s_res, e.relu != 0);
-        }
-        if (e.out_mode == SLQ_OUT_F32) {
-          float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.out) + m * g.Cout + cb);
+        for (int q4 = 0; q4 < 8; ++q4) {
+          float v[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        } else {
-          uint32_t pk[8];
-          const bool sgn = e.out_mode == SLQ_OUT_S8;
+          for (int b = 0; b < 4; ++b) {
+            const int j = 4 * q4 + b;
+            const ChanParam p = prm[ch * 32 + j];
+            v[b] = epi_value<W16>((int)lo[j], W16 ? (int)hi[j] : 0, Sf, p);
+            if (has_res) v[b] = epi_add_res(v[b], (rw[q4] >> (8 * b)) & 255u, res_signed, s_res);
+          }
+          if (f32_out) {
+            if (e.relu) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+              for (int b = 0; b < 4; ++b) v[b] = fmaxf(v[b], 0.f);
+            }
+            if (store_ok) of[q4] = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
             uint32_t w = 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b)
-              w |= (sgn ? epi_quant_s8(y[4 * j + b], inv_out) : epi_quant_u8(y[4 * j + b], inv_out)) << (8 * b);
-            pk[j] = w;
+              w |= (sgn_out ? epi_quant_s8(v[b], inv_out) : epi_quant_u8(v[b], inv_out)) << (8 * b);
+            pk[q4] = w;
           }
-          uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(e.out) + m * g.Cout + cb);
-          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        if (!f32_out) {
+          sts128(stg + stage_off(row, 2 * ch, g.bn_ch), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+          sts128(stg + stage_off(row, 2 * ch + 1, g.bn_ch), make_uint4(pk[4], pk[5], pk[6], pk[7]));
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(buf));  // 128 arrivals release the accumulator buffer
+      mbar_arrive(tempty_bar(grp));  // 128 arrivals release the accumulator buffer
+      if (has_res) mbar_arrive(rempty_bar(grp));
+      if (a.tma_out) {
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1 + grp, 128);
+        if (et == 0) {
+          tma_store_2d(&tmO, stg, n_tile * g.bn_ch, (int)(m_tile * kTileM));  // rows >= M are clipped
+          tma_store_commit();
+        }
+      }
     }
+    if (a.tma_out && et == 0) tma_store_wait_all();
   }
 
   // ---- teardown -----------------------------------------------------------------------------
@@ -433,6 +379,27 @@ static int get_encoders(EncodeTiledFn *tiled, EncodeIm2colFn *im2col) {
   }
   *tiled = f_tiled;
   *im2col = f_im2col;
+  return SLQ_OK;
+}
+
+// [M, Cout] u8 tensor (output or residual) as a tiled map with box = bn_ch channels x 128 pixels
+static int encode_out_map(CUtensorMap *tm, const void *ptr, const ConvGeom &g, const char *what) {
+  EncodeTiledFn enc_tiled;
+  EncodeIm2colFn enc_im2col;
+  int rc = get_encoders(&enc_tiled, &enc_im2col);
+  if (rc != SLQ_OK) return rc;
+  cuuint64_t dims[2] = {(cuuint64_t)g.Cout, (cuuint64_t)g.M};
+  cuuint64_t strides[1] = {(cuuint64_t)g.Cout};
+  cuuint32_t box[2] = {(cuuint32_t)g.bn_ch, (cuuint32_t)kTileM};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         g.bn_ch == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r);
+    return SLQ_ERR_CUDA;
+  }
   return SLQ_OK;
 }
 
@@ -494,7 +461,7 @@ static int build_tensor_maps(slq_conv *c) {
 }
 
 template <int SWZ, bool W16>
-static int launch_umma(slq_conv *c, const EpiDev &e, cudaStream_t st) {
+static int launch_umma(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {
   using C = Cfg<SWZ>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -509,7 +476,8 @@ static int launch_umma(slq_conv *c, const EpiDev &e, cudaStream_t st) {
   a.chunks_per_tap = c->g.Cin / SWZ;
   a.num_kb = c->g.kh * c->g.kw * a.chunks_per_tap;
   a.m_tiles = ceil_div(c->g.M, kTileM);
-  conv_umma_kernel<SWZ, W16><<<c->num_ctas, 256, C::kSmemBytes, st>>>(c->tmA, c->tmB, a);
+  a.tma_out = tma_out;
+  conv_umma_kernel<SWZ, W16><<<c->num_ctas, kThreads, C::kSmemBytes, st>>>(c->tmA, c->tmB, c->tmO, c->tmR, a);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }
@@ -532,6 +500,8 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
   c->in = in;
   c->wg = wg;
   c->swizzle = (d->Cin % 128 == 0) ? 128 : 64;
+  c->out_ptr = nullptr;
+  c->res_ptr = nullptr;
   const bool can_tile = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0;
   if (d->a_mode == SLQ_A_TILED && !can_tile) {
     delete c;
@@ -550,6 +520,8 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
       delete c;
       return rc;
     }
+    c->tmO = c->tmB;  // placeholders until the first launch names the output / residual buffers
+    c->tmR = c->tmB;
     const long long tiles = ceil_div(c->g.M, kTileM) * c->g.n_tiles;
     c->num_ctas = (int)std::min<long long>(tiles, sm_count());
     c->smem_bytes = c->swizzle == 128 ? Cfg<128>::kSmemBytes : Cfg<64>::kSmemBytes;
@@ -573,13 +545,25 @@ extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream
                 "slq_conv_launch: out/res must be 16-byte aligned");
   EpiDev e;
   e.wscale = ep->wscale; e.zf = ep->zf; e.bias = ep->bias; e.act_scales = ep->act_scales;
-  e.res = ep->res; e.out = ep->out; e.out_S = ep->out_S;
+  e.res = ep->out_mode == SLQ_OUT_ACC ? nullptr : ep->res;
+  e.out = ep->out; e.out_S = ep->out_S;
   e.in_id = ep->in_id; e.out_id = ep->out_id; e.res_id = ep->res_id;
   e.out_mode = ep->out_mode; e.relu = ep->relu; e.res_signed = ep->res_signed;
   e.Cout = c->g.Cout; e.w16 = c->g.w16; e.M = c->g.M;
   cudaStream_t st = (cudaStream_t)stream;
   if (c->desc.impl == SLQ_IMPL_SIMT) return launch_conv_simt(c->g, c->in, c->wg, e, st);
+  const int tma_out = (ep->out_mode == SLQ_OUT_U8 || ep->out_mode == SLQ_OUT_S8) ? 1 : 0;
+  if (tma_out && c->out_ptr != ep->out) {  // (re)encode the store map for this output buffer
+    int rc = encode_out_map(&c->tmO, ep->out, c->g, "out");
+    if (rc != SLQ_OK) return rc;
+    c->out_ptr = ep->out;
+  }
+  if (e.res && c->res_ptr != e.res) {
+    int rc = encode_out_map(&c->tmR, e.res, c->g, "residual");
+    if (rc != SLQ_OK) return rc;
+    c->res_ptr = e.res;
+  }
   if (c->swizzle == 128)
-    return c->g.w16 ? launch_umma<128, true>(c, e, st) : launch_umma<128, false>(c, e, st);
-  return c->g.w16 ? launch_umma<64, true>(c, e, st) : launch_umma<64, false>(c, e, st);
+    return c->g.w16 ? launch_umma<128, true>(c, e, tma_out, st) : launch_umma<128, false>(c, e, tma_out, st);
+  return c->g.w16 ? launch_umma<64, true>(c, e, tma_out, st) : launch_umma<64, false>(c, e, tma_out, st);
 }

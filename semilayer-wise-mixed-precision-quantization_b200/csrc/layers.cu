@@ -108,13 +108,12 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvGeom g, const uint8_
     return;
   }
   const float s_in = e.act_scales[e.in_id];
-  const float wsc = __fmul_rn(e.wscale[oc], s_in);
-  float y = epi_value((int)acc_lo, (int)acc_hi, g.w16 != 0, (float)(int)S, e.zf[oc], wsc, e.bias[oc]);
-  const bool has_res = e.res != nullptr;
-  const float s_res = has_res ? e.act_scales[e.res_id] : 0.f;
-  y = epi_residual_relu(y, has_res, has_res ? e.res[m * g.Cout + oc] : 0, e.res_signed != 0, s_res, e.relu != 0);
+  const ChanParam cp = make_chan_param(e.wscale[oc], e.zf[oc], e.bias[oc], s_in);
+  const float Sf = (float)(int)S;
+  float y = g.w16 ? epi_value<true>((int)acc_lo, (int)acc_hi, Sf, cp) : epi_value<false>((int)acc_lo, 0, Sf, cp);
+  if (e.res != nullptr) y = epi_add_res(y, e.res[m * g.Cout + oc], e.res_signed != 0, e.act_scales[e.res_id]);
   if (e.out_mode == SLQ_OUT_F32) {
-    reinterpret_cast<float *>(e.out)[m * g.Cout + oc] = y;
+    reinterpret_cast<float *>(e.out)[m * g.Cout + oc] = e.relu ? fmaxf(y, 0.f) : y;
   } else {
     const float inv = __fdiv_rn(1.0f, e.act_scales[e.out_id]);
     const uint32_t q = e.out_mode == SLQ_OUT_S8 ? epi_quant_s8(y, inv) : epi_quant_u8(y, inv);
@@ -228,6 +227,14 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float *__restrict_
   }
 }
 
+int launch_stem_pool(const float *y, int N, int Hc, int Wc, int Hp, int Wp, const float *act_scales,
+                     int out_id, void *out, int out_mode, cudaStream_t st) {
+  const long long total = (long long)N * Hp * Wp * 16;
+  stem_pool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode);
+  SLQ_LAUNCH_CHECK();
+  return SLQ_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // Tail: global average pool over u8 NHWC + fc
 // ------------------------------------------------------------------------------------------
@@ -248,24 +255,44 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const uint8_t *__restrict_
   *reinterpret_cast<float4 *>(pooled + (long long)n * C + c4 * 4) = o;
 }
 
+// logits[n, o] = sum_c pooled[n, c] * fw[o, c] + fb[o]: 32 x 64 output tile per CTA, K chunks of 32
 __global__ void __launch_bounds__(256) fc_kernel(const float *__restrict__ pooled, int N, int C,
                                                  const float *__restrict__ fw, const float *__restrict__ fb,
                                                  int O, float *__restrict__ logits) {
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= (long long)N * O) return;
-  const int n = (int)(warp / O), o = (int)(warp % O);
-  const float4 *a = reinterpret_cast<const float4 *>(pooled + (long long)n * C);
-  const float4 *b = reinterpret_cast<const float4 *>(fw + (long long)o * C);
-  float acc = 0.f;
-  for (int i = lane; i < C / 4; i += 32) {
-    const float4 u = __ldg(a + i), v = __ldg(b + i);
-    acc = fmaf(u.x, v.x, acc); acc = fmaf(u.y, v.y, acc);
-    acc = fmaf(u.z, v.z, acc); acc = fmaf(u.w, v.w, acc);
+  __shared__ float As[32][33];
+  __shared__ float Bs[64][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> 4 outputs o, ty -> 2 images n
+  const int n0 = blockIdx.y * 32, o0 = blockIdx.x * 64;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      As[r][c] = (n0 + r < N && c0 + c < C) ? pooled[(long long)(n0 + r) * C + c0 + c] : 0.f;
+    }
+    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
+      const int r = i >> 5, c = i & 31;
+      Bs[r][c] = (o0 + r < O && c0 + c < C) ? fw[(long long)(o0 + r) * C + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      const float a0 = As[ty * 2][c], a1 = As[ty * 2 + 1][c];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float b = Bs[tx + 16 * j][c];
+        acc[0][j] = fmaf(a0, b, acc[0][j]);
+        acc[1][j] = fmaf(a1, b, acc[1][j]);
+      }
+    }
+    __syncthreads();
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-  if (lane == 0) logits[(long long)n * O + o] = acc + fb[o];
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + ty * 2 + i, o = o0 + tx + 16 * j;
+      if (n < N && o < O) logits[(long long)n * O + o] = acc[i][j] + fb[o];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -353,10 +380,7 @@ extern "C" int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W,
   dim3 grid((unsigned)ceil_div(Wc, kStemTile), (unsigned)ceil_div(Hc, kStemTile), (unsigned)N);
   stem_conv_kernel<<<grid, 256, 0, st>>>(x, N, H, W, Hc, Wc, w, bn_a, bn_b, scratch);
   SLQ_LAUNCH_CHECK();
-  const long long total = (long long)N * Hp * Wp * 16;
-  stem_pool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(scratch, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode);
-  SLQ_LAUNCH_CHECK();
-  return SLQ_OK;
+  return launch_stem_pool(scratch, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode, st);
 }
 
 extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C,
@@ -369,8 +393,8 @@ extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t
   dim3 g1((unsigned)ceil_div(C / 4, 256), (unsigned)N);
   avgpool_kernel<<<g1, 256, 0, st>>>(x, HW, C, act_scales, in_id, pooled);
   SLQ_LAUNCH_CHECK();
-  const long long threads = (long long)N * O * 32;
-  fc_kernel<<<(unsigned)ceil_div(threads, 256), 256, 0, st>>>(pooled, N, C, fc_w, fc_b, O, logits);
+  dim3 g2((unsigned)ceil_div(O, 64), (unsigned)ceil_div(N, 32));
+  fc_kernel<<<g2, 256, 0, st>>>(pooled, N, C, fc_w, fc_b, O, logits);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }

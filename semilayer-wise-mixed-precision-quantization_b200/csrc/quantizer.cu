@@ -39,6 +39,7 @@ constexpr int kVpt = 9;      // float4 per thread held in registers: 36 floats
 
 struct Affine {  // result of Appendix A.1-A.4 for one row
   float s32;
+  float inv;  // SLQ_DIV_RECIP multiplier: float32(1.0 / scale64), what ATen computes on the host
   float zf;
   long long z;
   int ok;  // 0: zero range
@@ -52,6 +53,7 @@ __device__ __forceinline__ Affine derive_affine(float mnf, float mxf, int bit) {
   a.ok = (scale != 0.0);
   const double zd = a.ok ? rint(__ddiv_rn(mn, scale)) : 0.0;   // functions.py:40 (half-even)
   a.s32 = __double2float_rn(scale);
+  a.inv = __double2float_rn(__ddiv_rn(1.0, scale));
   a.zf = __double2float_rn(zd);
   a.z = (long long)zd;
   return a;
@@ -170,7 +172,7 @@ __global__ void __launch_bounds__(kBlock) quantize_rows_kernel(
     }
     return;
   }
-  const float inv = __fdiv_rn(1.0f, a.s32);
+  const float inv = a.inv;
   const int maxcode = (1 << bit) - 1;
   uint8_t *row_codes = codes ? codes + code_offsets[job] : nullptr;
   float4 *out4 = reinterpret_cast<float4 *>(row);
@@ -236,7 +238,7 @@ __global__ void __launch_bounds__(kBlock) quantize_rows_generic_kernel(
     }
     return;
   }
-  const float inv = __fdiv_rn(1.0f, a.s32);
+  const float inv = a.inv;
   const int maxcode = (1 << bit) - 1;
   uint8_t *row_codes = codes ? codes + code_offsets[job] : nullptr;
   int bad = 0;

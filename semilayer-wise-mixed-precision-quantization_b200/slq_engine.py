@@ -90,12 +90,14 @@ class _ConvOp:
 
 
 class Engine:
-    def __init__(self, net, N, H, W, device, impl=L.IMPL_UMMA, a_mode=L.A_AUTO):
+    def __init__(self, net, N, H, W, device, impl=L.IMPL_UMMA, a_mode=L.A_AUTO, stem="umma"):
         if device.type != "cuda":
             raise RuntimeError("slq Engine needs a CUDA device")
         self.lib = L.lib()
         self.net, self.N, self.H, self.W, self.device = net, N, H, W, device
         self.impl, self.a_mode = impl, a_mode
+        self.stem_kind = stem  # "umma": tcgen05 fp16 stem; "simt": exact-fp32 CUDA-core stem
+        self.stem = None
         self.epoch = -1
         self.kernel_launches = 0
         with torch.cuda.device(device):
@@ -115,6 +117,14 @@ class Engine:
         Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
         self.act, self.act_signed, self.ops = [], [], []
         self.stem_scratch = torch.empty(N * Hc * Wc * 64, dtype=torch.float32, device=dev)
+        if self.stem_kind == "umma" and Wc > 128:
+            self.stem_kind = "simt"  # one output row per 128-pixel tile: inputs wider than 256 px
+        if self.stem_kind == "umma":
+            nbytes = self.lib.slq_stem_workspace_bytes(N, self.H, self.W)
+            self.stem_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            h = ctypes.c_void_p()
+            L.check(self.lib.slq_stem_create(N, self.H, self.W, self.stem_ws.data_ptr(), ctypes.byref(h)))
+            self.stem = h
         x_id = self._new_act((N, Hp, Wp, 64))
         h, w = Hp, Wp
         max_out = N * Hp * Wp * 64
@@ -194,6 +204,8 @@ class Engine:
                 op.bias = b.contiguous()
                 op.epi = {}
             self.stem_w = self.net.conv1.weight.detach().contiguous()
+            if self.stem is not None:
+                L.check(lib.slq_stem_set_weights(self.stem, self.stem_w.data_ptr(), stream))
             self.stem_a, self.stem_b = self._fold_bn(self.net.bn1)
             self.fc_w = self.net.fc.weight.detach().contiguous()
             self.fc_b = self.net.fc.bias.detach().contiguous()
@@ -233,9 +245,7 @@ class Engine:
             st = L.current_stream(self.device)
             sc, tmp, f32 = self.act_scales.data_ptr(), self.absmax_tmp.data_ptr(), self.f32_scratch
             n0 = self.act[0].numel()
-            L.check(lib.slq_stem_forward(x.data_ptr(), self.N, self.H, self.W, self.stem_w.data_ptr(),
-                                         self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
-                                         self.stem_scratch.data_ptr(), f32.data_ptr(), L.OUT_F32, st))
+            self._stem(x.data_ptr(), f32.data_ptr(), L.OUT_F32, st)
             L.check(lib.slq_absmax_scale(f32.data_ptr(), n0, sc, 0, 255, tmp, st))
             L.check(lib.slq_quantize_act(f32.data_ptr(), n0, sc, 0, 0, self.act[0].data_ptr(), st))
             for op in self.ops:
@@ -258,9 +268,7 @@ class Engine:
     def launch_all(self, x_ptr, st):
         lib = self.lib
         sc = self.act_scales.data_ptr()
-        L.check(lib.slq_stem_forward(x_ptr, self.N, self.H, self.W, self.stem_w.data_ptr(),
-                                     self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
-                                     self.stem_scratch.data_ptr(), self.act[0].data_ptr(), L.OUT_U8, st))
+        self._stem(x_ptr, self.act[0].data_ptr(), L.OUT_U8, st)
         for op in self.ops:
             mode = L.OUT_S8 if op.signed else L.OUT_U8
             e = self._epilogue(op, mode, self.act[op.out_id].data_ptr())
@@ -268,7 +276,17 @@ class Engine:
         L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
                                      sc, self.final_id, self.fc_w.data_ptr(), self.fc_b.data_ptr(),
                                      self.logits.shape[1], self.pooled.data_ptr(), self.logits.data_ptr(), st))
-        self.kernel_launches = 2 + len(self.ops) + 2
+        self.kernel_launches = (3 if self.stem is not None else 2) + len(self.ops) + 2
+
+    def _stem(self, x_ptr, out_ptr, mode, st):
+        lib, sc = self.lib, self.act_scales.data_ptr()
+        if self.stem is not None:
+            L.check(lib.slq_stem_launch(self.stem, x_ptr, self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
+                                        out_ptr, mode, self.stem_scratch.data_ptr(), st))
+        else:
+            L.check(lib.slq_stem_forward(x_ptr, self.N, self.H, self.W, self.stem_w.data_ptr(),
+                                         self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
+                                         self.stem_scratch.data_ptr(), out_ptr, mode, st))
 
     # ------------------------------------------------------------------------------------------
     def capture_graph(self, x_static):
@@ -303,5 +321,8 @@ class Engine:
                 if getattr(op, "handle", None) is not None:
                     self.lib.slq_conv_destroy(op.handle)
                     op.handle = None
+            if getattr(self, "stem", None) is not None:
+                self.lib.slq_stem_destroy(self.stem)
+                self.stem = None
         except Exception:
             pass

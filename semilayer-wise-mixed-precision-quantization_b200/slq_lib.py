@@ -48,6 +48,11 @@ SIGNATURES = {
     "slq_conv_destroy": (None, [_vp]),
     "slq_conv_launch": (ctypes.c_int, [_vp, ctypes.POINTER(Epilogue), _vp]),
     "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "slq_stem_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "slq_stem_create": (ctypes.c_int, [_i32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),
+    "slq_stem_destroy": (None, [_vp]),
+    "slq_stem_set_weights": (ctypes.c_int, [_vp, _vp, _vp]),
+    "slq_stem_launch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "slq_tail_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "slq_absmax_scale": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "slq_quantize_act": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),

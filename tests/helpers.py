@@ -146,27 +146,14 @@ class ConvCase:
 
 def oracle_epilogue_case(case, wscale, zf, bias, scales, in_id, out_id, res, res_id, res_signed, relu, mode):
     import slq_lib as L
-    f = np.float32
     lo, hi, S = case.oracle_acc()
-    accf = lo.astype(np.float32)
-    if hi is not None:
-        accf = ((hi.astype(np.float32) * f(256.0)).astype(f) + accf).astype(f)
-    Sf = S.astype(np.float32)[:, None]
-    v = (accf + (zf.astype(f)[None, :] * Sf).astype(f)).astype(f)
-    sc = (wscale.astype(f) * f(scales[in_id])).astype(f)
-    y = ((v * sc[None, :]).astype(f) + bias.astype(f)[None, :]).astype(f)
-    if res is not None:
-        r = res.view(np.int8).astype(f) if res_signed else res.astype(f)
-        y = (y + (r * f(scales[res_id])).astype(f)).astype(f)
-    if relu:
-        y = np.maximum(y, f(0))
+    y = so.epilogue(lo, S, zf, wscale, bias, scales[in_id], res, scales[res_id] if res is not None else None,
+                    relu=bool(relu) and mode == L.OUT_F32, acc_hi=hi, res_signed=bool(res_signed))
     if mode == L.OUT_F32:
         return y
-    inv = f(1.0) / f(scales[out_id])
-    q = np.rint((y * inv).astype(f))
     if mode == L.OUT_S8:
-        return np.clip(q, -127, 127).astype(np.int8).view(np.uint8)
-    return np.clip(q, 0, 255).astype(np.uint8)
+        return so.requant_s8(y, scales[out_id])
+    return so.requant_u8(y, scales[out_id])
 
 
 def rel_l2(a, b):

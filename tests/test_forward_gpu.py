@@ -95,8 +95,8 @@ def test_activation_pipeline_matches_numpy_oracle_first_block():
     assert abs(float(t.max()) / 255.0 - float(s0)) <= 1e-5 * float(s0) + 1e-9
     q = so.requant_u8(t, s0)
     got = eng.act[0].cpu().numpy().astype(np.int32)
-    assert np.abs(got - q.astype(np.int32)).max() <= 1  # fp32 summation order differs from cuDNN
-    assert (got != q).mean() < 0.02
+    assert np.abs(got - q.astype(np.int32)).max() <= 1  # fp16 tensor-core operands / summation order
+    assert (got != q).mean() < 0.05
 
 
 def test_batch_32_top1_agreement_and_dropin_evaluate():
@@ -142,3 +142,30 @@ def test_weight_mutation_is_seen_by_the_next_forward():
         net.load_state_dict(sd)
         l2 = net(x).clone()
         assert torch.equal(l0, l2)
+
+
+def test_tensor_core_stem_matches_exact_fp32_stem():
+    """The tcgen05 stem (fp16 operands, fp32 accumulate) against the exact-fp32 CUDA-core stem:
+    same static scale to 1e-3, u8 activations within one level, fp32 pre-quantisation values to 2e-3."""
+    import slq_engine
+    import slq_lib as L
+    net = build_p0_model("resnet18", "cuda")
+    for n in (2, 5):
+        g = torch.Generator().manual_seed(n)
+        x = torch.randn(n, 3, 224, 224, generator=g).cuda()
+        res = {}
+        for kind in ("umma", "simt"):
+            eng = slq_engine.Engine(net, n, 224, 224, x.device, stem=kind)
+            eng.refresh_weights()
+            assert (eng.stem is not None) == (kind == "umma")
+            eng._stem(x.data_ptr(), eng.f32_scratch.data_ptr(), L.OUT_F32, L.current_stream())
+            torch.cuda.synchronize()
+            f32 = eng.f32_scratch[:eng.act[0].numel()].clone()
+            eng.calibrate(x)
+            eng.forward(x)
+            res[kind] = (f32, eng.act[0].clone(), float(eng.act_scales[0]))
+        fa, fb = res["umma"][0], res["simt"][0]
+        assert float((fa - fb).abs().max()) <= 2e-3 * float(fb.abs().max())
+        assert abs(res["umma"][2] - res["simt"][2]) <= 1e-3 * res["simt"][2]
+        d = (res["umma"][1].int() - res["simt"][1].int()).abs()
+        assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.05

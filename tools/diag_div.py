@@ -39,7 +39,7 @@ for trial in range(40):
     tot["mul: f32(f64(k) * scale64)"] = tot.get("mul: f32(f64(k) * scale64)", 0) + int(((s_gpu.astype(np.float64) * scale).astype(np.float32).view(np.uint32) != m_gpu.view(np.uint32)).sum())
     # the whole chain as the reference writes it, on the device
     full_gpu = ((((t / scale) + z).round() - z) * scale).cpu().numpy()
-    chain = (((((w * np.float32(1.0 / scale)).astype(np.float32) + np.float32(z)).astype(np.float32)))
+    chain = ((w * np.float32(1.0 / scale)).astype(np.float32) + np.float32(z)).astype(np.float32)
     k = (np.rint(chain) - np.float32(z)).astype(np.float32)
     tot["chain: H(1.0/scale64)"] = tot.get("chain: H(1.0/scale64)", 0) + int(((k * s32).astype(np.float32).view(np.uint32) != full_gpu.view(np.uint32)).sum())
     n_el += K
