@@ -203,27 +203,48 @@ def fma32(a, b, c):
     return np.where(tie & (err != 0) & toward, other, r).astype(np.float32)
 
 
+def _epilogue_core(acc, S, zf, wscale, bias, s_in, inv_out, res_u8, s_res, acc_hi, res_signed):
+    f = np.float32
+    wsc = (wscale.astype(f) * f(s_in)).astype(f)
+    zw = (zf.astype(f) * wsc).astype(f)
+    b = bias.astype(f)
+    if inv_out is not None:  # quantised output: the re-quantisation multiply is folded per channel
+        inv = f(inv_out)
+        wsc, zw, b = (wsc * inv).astype(f), (zw * inv).astype(f), (b * inv).astype(f)
+    accf = acc.astype(f)
+    if acc_hi is not None:
+        accf = fma32(acc_hi.astype(f), f(256.0), accf)
+    c2 = fma32(S.astype(f)[:, None], zw[None, :], b[None, :])
+    y = fma32(accf, wsc[None, :], c2)
+    if res_u8 is not None:
+        r = res_u8.view(np.int8).astype(f) if res_signed else res_u8.astype(f)
+        sr = f(s_res) if inv_out is None else (f(s_res) * f(inv_out)).astype(f)
+        y = fma32(r, sr, y)
+    return y
+
+
 def epilogue(acc, S, zf, wscale, bias, s_in, res_u8=None, s_res=None, relu=True, acc_hi=None,
              res_signed=False):
-    """fp32 epilogue exactly as csrc/epilogue.cuh computes it (fma = one rounding):
+    """fp32-output epilogue exactly as csrc/epilogue.cuh computes it (fma = one rounding):
          wsc = wscale*s_in ; zw = zf*wsc
          accf = f32(acc) [two limbs: fma(f32(hi), 256, f32(lo))]
          y = fma(accf, wsc, fma(f32(S), zw, bias)) ; y = fma(f32(res), s_res, y)
        Returns the fp32 output (ReLU applied when relu)."""
-    f = np.float32
-    wsc = (wscale.astype(f) * f(s_in)).astype(f)
-    zw = (zf.astype(f) * wsc).astype(f)
-    accf = acc.astype(f)
-    if acc_hi is not None:
-        accf = fma32(acc_hi.astype(f), f(256.0), accf)
-    c2 = fma32(S.astype(f)[:, None], zw[None, :], bias.astype(f)[None, :])
-    y = fma32(accf, wsc[None, :], c2)
-    if res_u8 is not None:
-        r = res_u8.view(np.int8).astype(f) if res_signed else res_u8.astype(f)
-        y = fma32(r, f(s_res), y)
-    if relu:
-        y = np.maximum(y, f(0))
-    return y
+    y = _epilogue_core(acc, S, zf, wscale, bias, s_in, None, res_u8, s_res, acc_hi, res_signed)
+    return np.maximum(y, np.float32(0)) if relu else y
+
+
+def epilogue_q(acc, S, zf, wscale, bias, s_in, s_out, res_u8=None, s_res=None, acc_hi=None,
+               res_signed=False, signed_out=False):
+    """u8 / s8-output epilogue of csrc/epilogue.cuh: same chain with inv = 1/s_out folded into the
+    per-channel constants (A = wsc*inv, Z = zw*inv, B = bias*inv, sr = s_res*inv), then
+    sat(rint(y)).  Saturation at 0 is the ReLU of u8 tensors.  Returns raw bytes (uint8)."""
+    inv = np.float32(1.0) / np.float32(s_out)
+    y = _epilogue_core(acc, S, zf, wscale, bias, s_in, inv, res_u8, s_res, acc_hi, res_signed)
+    q = np.nan_to_num(np.rint(y), nan=0.0)
+    if signed_out:
+        return np.clip(q, -128, 127).astype(np.int8).view(np.uint8)
+    return np.clip(q, 0, 255).astype(np.uint8)
 
 
 def requant_u8(y, s_out):

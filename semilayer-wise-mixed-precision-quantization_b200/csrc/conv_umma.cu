@@ -10,14 +10,18 @@
 //   One extra "ones" B row per tile makes the tensor core also produce the window sum
 //   S[m] = sum_k A[m, k] that the zero-point correction z[oc]*S[m] needs.
 //
-// Persistent, warp-specialised CTA (384 threads, 1 CTA/SM):
-//   warp 0     TMA producer (A, B)    one lane; smem ring of kStages x {A 128xSWZ, B (bn+16)xSWZ}
-//   warp 1     tcgen05.mma issuer     one lane; accumulators double-buffered in TMEM (2 x 256 cols)
-//   warp 2     TMEM allocator
-//   warp 3     residual producer      one lane; TMA-loads the identity tile of the block
-//   warps 4-7  epilogue group 0  \  tile i -> group i&1: tcgen05.ld -> dequant + folded BN + residual
-//   warps 8-11 epilogue group 1  /  + ReLU -> u8 into a swizzled smem tile -> ONE TMA store per tile
-// so the global traffic of the epilogue is fully coalesced 128-byte lines in both directions.
+// Persistent, warp-specialised CTA (640 threads, 1 CTA/SM):
+//   warp 0      TMA producer (A, B)    one lane; smem ring of kStages x {A 128xSWZ, B (bn+16)xSWZ}
+//   warp 1      tcgen05.mma issuer     one lane; accumulators double-buffered in TMEM (2 x 256 cols)
+//   warp 2      TMEM allocator
+//   warp 3      residual producer      one lane; TMA-loads the identity tile of the block
+//   warps 4-11  epilogue team 0  \  tile i -> team i&1 (= accumulator buffer i&1).  A team is 8 warps:
+//   warps 12-19 epilogue team 1  /  two per TMEM lane quarter, each taking half of the tile's channels:
+//               tcgen05.ld -> dequant + folded BN + residual + ReLU -> u8 into a swizzled smem tile
+//               -> ONE TMA store per tile, so the epilogue's global traffic is coalesced 128-byte
+//               lines in both directions.  The epilogue is the issue-bound part of the small-K layers
+//               (16 warps = 4 per scheduler keep it near one instruction per cycle per scheduler) and is
+//               compiled per (output kind, residual kind) so that no mode branch survives in the loop.
 #include <algorithm>
 #include <new>
 
@@ -26,7 +30,8 @@
 
 namespace slq {
 
-constexpr int kThreads = 384;
+constexpr int kThreads = 640;
+constexpr int kTeam = 256;  // threads of one epilogue team
 constexpr int kOutTileBytes = kTileM * 128;  // u8 output / residual staging tile (128 rows x <=128 B)
 
 template <int SWZ>
@@ -66,7 +71,10 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c, int bn_ch) {
                       : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
 
-template <int SWZ, bool W16>
+// OUT: SLQ_OUT_*;  RES: residual kind
+constexpr int kResNone = 0, kResU8 = 1, kResS8 = 2, kResDyn = 3;  // Dyn: decided at run time (fp32/raw outputs)
+
+template <int SWZ, bool W16, int OUT, int RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
@@ -91,7 +99,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int bn_cols = g.bn_cols;
   const int umma_n = bn_cols + 16;
   const long long total_tiles = a.m_tiles * g.n_tiles;
-  const bool has_res = e.res != nullptr;
+  const bool has_res = RES == kResDyn ? (e.res != nullptr) : (RES != kResNone);
 
   // ---- one-time setup -----------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -107,9 +115,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), kTeam);
       mbar_init(rfull_bar(b), 1);
-      mbar_init(rempty_bar(b), 128);
+      mbar_init(rempty_bar(b), kTeam);
     }
     fence_barrier_init();
   }
@@ -215,118 +223,125 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue (2 groups of 4 warps) ===========================
-    const int grp = (warp - 4) >> 2;
+    // ================================ epilogue (2 teams of 8 warps) ============================
+    constexpr bool kQuant = OUT == SLQ_OUT_U8 || OUT == SLQ_OUT_S8;
+    constexpr int CW = W16 ? 16 : 32;              // accumulator columns per TMEM load
+    const int team = (warp - 4) >> 3;              // == accumulator buffer
+    const int half = ((warp - 4) >> 2) & 1;        // which half of the tile's channel units
     const int wq = warp & 3;                       // TMEM lane quarter this warp may touch
-    const int et = threadIdx.x - 128 - grp * 128;  // 0..127 inside the group
+    const int et = threadIdx.x - 128 - team * kTeam;  // 0..255 inside the team
     const int row = wq * 32 + lane;                // tile row == TMEM lane
-    ChanParam *prm = reinterpret_cast<ChanParam *>(smem + C::kPrmOff) + grp * 128;
-    const uint32_t stg = smem_base + C::kOutOff + grp * kOutTileBytes;
-    const uint32_t rsb = smem_base + C::kResOff + grp * kOutTileBytes;
+    ChanParam *prm = reinterpret_cast<ChanParam *>(smem + C::kPrmOff) + team * 128;
+    const uint32_t prm_s = smem_base + C::kPrmOff + team * 128 * 16;
+    const uint32_t stg = smem_base + C::kOutOff + team * kOutTileBytes;
+    const uint32_t rsb = smem_base + C::kResOff + team * kOutTileBytes;
     float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
-    if (e.out_mode != SLQ_OUT_ACC) {
+    if (OUT != SLQ_OUT_ACC) {
       s_in = e.act_scales[e.in_id];
-      if (has_res) s_res = e.act_scales[e.res_id];
-      if (e.out_mode != SLQ_OUT_F32) inv_out = __fdiv_rn(1.0f, e.act_scales[e.out_id]);
+      if (kQuant) inv_out = __fdiv_rn(1.0f, e.act_scales[e.out_id]);
+      if (has_res) s_res = kQuant ? __fmul_rn(e.act_scales[e.res_id], inv_out) : e.act_scales[e.res_id];
     }
-    const bool res_signed = e.res_signed != 0;
-    const bool sgn_out = e.out_mode == SLQ_OUT_S8;
-    const int chunks = g.bn_ch / 32;
+    const bool res_signed = RES == kResDyn ? (e.res_signed != 0) : (RES == kResS8);
+    const int units = g.bn_ch / CW;
+    const int u0 = half * (units >> 1), u1 = u0 + (units >> 1);
     int last_n_tile = -1;
-    long long it = grp;
-    for (long long tile = blockIdx.x + (long long)grp * gridDim.x; tile < total_tiles;
+    long long it = team;
+    for (long long tile = blockIdx.x + (long long)team * gridDim.x; tile < total_tiles;
          tile += 2LL * gridDim.x, it += 2) {
       const long long m_tile = tile / g.n_tiles;
       const int n_tile = (int)(tile % g.n_tiles);
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
-      // staging tile free again? (the previous TMA store of this group has read it)
+      // staging tile free again? (the previous TMA store of this team has read it)
       if (a.tma_out && et == 0) tma_store_wait_read();
-      named_bar_sync(1 + grp, 128);
-      if (n_tile != last_n_tile && e.out_mode != SLQ_OUT_ACC) {
+      named_bar_sync(1 + team, kTeam);
+      if (n_tile != last_n_tile && OUT != SLQ_OUT_ACC) {
         if (et < g.bn_ch) {
           const int oc = n_tile * g.bn_ch + et;
           ChanParam p = {0.f, 0.f, 0.f, 0.f};
-          if (oc < g.Cout) p = make_chan_param(e.wscale[oc], e.zf[oc], e.bias[oc], s_in);
+          if (oc < g.Cout) p = make_chan_param(e.wscale[oc], e.zf[oc], e.bias[oc], s_in, inv_out, kQuant);
           prm[et] = p;
         }
         last_n_tile = n_tile;
+        named_bar_sync(1 + team, kTeam);
       }
-      named_bar_sync(1 + grp, 128);
-      mbar_wait(tfull_bar(grp), ph);
+      mbar_wait(tfull_bar(team), ph);
       tc_fence_after();
-      if (has_res) mbar_wait(rfull_bar(grp), ph);
-      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + grp * kAccStride;
+      if (has_res) mbar_wait(rfull_bar(team), ph);
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + team * kAccStride;
       const long long m = m_tile * kTileM + row;
       const bool valid = m < g.M;
       const uint32_t S_raw = tmem_ld1(trow + bn_cols);
       tmem_ld_wait();
       const float Sf = (float)(int)S_raw;
-      if (e.out_mode == SLQ_OUT_ACC && e.out_S && valid && n_tile == 0) e.out_S[m] = (int)S_raw;
-      for (int ch = 0; ch < chunks; ++ch) {
-        uint32_t lo[32], hi[32];
-        tmem_ld32(trow + ch * 32, lo);
-        if (W16) tmem_ld32(trow + 64 + ch * 32, hi);
+      if (OUT == SLQ_OUT_ACC && e.out_S && valid && n_tile == 0 && half == 0) e.out_S[m] = (int)S_raw;
+      for (int u = u0; u < u1; ++u) {
+        uint32_t lo[CW], hi[CW];
+        tmem_ld<CW>(trow + u * CW, lo);
+        if constexpr (W16) tmem_ld<CW>(trow + 64 + u * CW, hi);
+        uint32_t rw[CW / 4];
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < CW / 16; ++i) {
+            const uint4 r = lds128(rsb + stage_off(row, u * (CW / 16) + i, g.bn_ch));
+            rw[4 * i] = r.x; rw[4 * i + 1] = r.y; rw[4 * i + 2] = r.z; rw[4 * i + 3] = r.w;
+          }
+        }
         tmem_ld_wait();
-        const int cb = n_tile * g.bn_ch + ch * 32;  // first output channel of this chunk
-        if (e.out_mode == SLQ_OUT_ACC) {
+        const int cb = n_tile * g.bn_ch + u * CW;  // first output channel of this unit
+        if (OUT == SLQ_OUT_ACC) {
           if (!valid || cb >= g.Cout) continue;
           const long long ld = (long long)(W16 ? 2 : 1) * g.Cout;
           int4 *o = reinterpret_cast<int4 *>(reinterpret_cast<int32_t *>(e.out) + m * ld + cb);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_int4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+          for (int j = 0; j < CW / 4; ++j) o[j] = make_int4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
           if (W16) {
             int4 *oh = reinterpret_cast<int4 *>(reinterpret_cast<int32_t *>(e.out) + m * ld + g.Cout + cb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) oh[j] = make_int4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            for (int j = 0; j < CW / 4; ++j) oh[j] = make_int4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
           }
           continue;
         }
-        uint32_t rw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (has_res) {
-          const uint4 r0 = lds128(rsb + stage_off(row, 2 * ch, g.bn_ch));
-          const uint4 r1 = lds128(rsb + stage_off(row, 2 * ch + 1, g.bn_ch));
-          rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w;
-          rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
-        }
-        const bool f32_out = e.out_mode == SLQ_OUT_F32;
         const bool store_ok = valid && cb < g.Cout;
         float4 *of = reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.out) + m * g.Cout + cb);
-        uint32_t pk[8];
+        uint32_t pk[CW / 4];
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
+        for (int q4 = 0; q4 < CW / 4; ++q4) {
           float v[4];
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
             const int j = 4 * q4 + b;
-            const ChanParam p = prm[ch * 32 + j];
+            const uint4 pr = lds128(prm_s + (uint32_t)(u * CW + j) * 16);  // warp-wide broadcast
+            ChanParam p;
+            p.wsc = __uint_as_float(pr.x); p.zw = __uint_as_float(pr.y); p.bias = __uint_as_float(pr.z);
             v[b] = epi_value<W16>((int)lo[j], W16 ? (int)hi[j] : 0, Sf, p);
-            if (has_res) v[b] = epi_add_res(v[b], (rw[q4] >> (8 * b)) & 255u, res_signed, s_res);
+            if (has_res) {
+              const uint32_t byte = (rw[q4] >> (8 * b)) & 255u;
+              v[b] = epi_add_res(v[b], byte, res_signed, s_res);
+            }
           }
-          if (f32_out) {
+          if (!kQuant) {
             if (e.relu) {
 #pragma unroll
               for (int b = 0; b < 4; ++b) v[b] = fmaxf(v[b], 0.f);
             }
             if (store_ok) of[q4] = make_float4(v[0], v[1], v[2], v[3]);
           } else {
-            uint32_t w = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-              w |= (sgn_out ? epi_quant_s8(v[b], inv_out) : epi_quant_u8(v[b], inv_out)) << (8 * b);
-            pk[q4] = w;
+            pk[q4] = epi_pack4<OUT == SLQ_OUT_S8>(v[0], v[1], v[2], v[3]);
           }
         }
-        if (!f32_out) {
-          sts128(stg + stage_off(row, 2 * ch, g.bn_ch), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-          sts128(stg + stage_off(row, 2 * ch + 1, g.bn_ch), make_uint4(pk[4], pk[5], pk[6], pk[7]));
+        if (kQuant) {
+#pragma unroll
+          for (int i = 0; i < CW / 16; ++i)
+            sts128(stg + stage_off(row, u * (CW / 16) + i, g.bn_ch),
+                   make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]));
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(grp));  // 128 arrivals release the accumulator buffer
-      if (has_res) mbar_arrive(rempty_bar(grp));
+      mbar_arrive(tempty_bar(team));  // kTeam arrivals release the accumulator buffer
+      if (has_res) mbar_arrive(rempty_bar(team));
       if (a.tma_out) {
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1 + grp, 128);
+        named_bar_sync(1 + team, kTeam);
         if (et == 0) {
           tma_store_2d(&tmO, stg, n_tile * g.bn_ch, (int)(m_tile * kTileM));  // rows >= M are clipped
           tma_store_commit();
@@ -460,13 +475,13 @@ static int build_tensor_maps(slq_conv *c) {
   return SLQ_OK;
 }
 
-template <int SWZ, bool W16>
-static int launch_umma(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {
+template <int SWZ, bool W16, int OUT, int RES>
+static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {
   using C = Cfg<SWZ>;
   static bool attr_done = false;
   if (!attr_done) {
-    SLQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<SWZ, W16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  C::kSmemBytes));
+    SLQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<SWZ, W16, OUT, RES>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
   KernelArgs a;
@@ -477,9 +492,30 @@ static int launch_umma(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t s
   a.num_kb = c->g.kh * c->g.kw * a.chunks_per_tap;
   a.m_tiles = ceil_div(c->g.M, kTileM);
   a.tma_out = tma_out;
-  conv_umma_kernel<SWZ, W16><<<c->num_ctas, kThreads, C::kSmemBytes, st>>>(c->tmA, c->tmB, c->tmO, c->tmR, a);
+  conv_umma_kernel<SWZ, W16, OUT, RES><<<c->num_ctas, kThreads, C::kSmemBytes, st>>>(c->tmA, c->tmB, c->tmO,
+                                                                                   c->tmR, a);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
+}
+
+// picks the compiled (output kind, residual kind) variant
+template <int SWZ, bool W16>
+static int launch_umma(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {
+  const int res = e.res == nullptr ? kResNone : (e.res_signed ? kResS8 : kResU8);
+  switch (e.out_mode) {
+    case SLQ_OUT_U8:
+      if (res == kResNone) return launch_one<SWZ, W16, SLQ_OUT_U8, kResNone>(c, e, tma_out, st);
+      if (res == kResU8) return launch_one<SWZ, W16, SLQ_OUT_U8, kResU8>(c, e, tma_out, st);
+      return launch_one<SWZ, W16, SLQ_OUT_U8, kResS8>(c, e, tma_out, st);
+    case SLQ_OUT_S8:
+      if (res == kResNone) return launch_one<SWZ, W16, SLQ_OUT_S8, kResNone>(c, e, tma_out, st);
+      if (res == kResU8) return launch_one<SWZ, W16, SLQ_OUT_S8, kResU8>(c, e, tma_out, st);
+      return launch_one<SWZ, W16, SLQ_OUT_S8, kResS8>(c, e, tma_out, st);
+    case SLQ_OUT_F32:
+      return launch_one<SWZ, W16, SLQ_OUT_F32, kResDyn>(c, e, tma_out, st);
+    default:
+      return launch_one<SWZ, W16, SLQ_OUT_ACC, kResNone>(c, e, tma_out, st);
+  }
 }
 
 }  // namespace slq

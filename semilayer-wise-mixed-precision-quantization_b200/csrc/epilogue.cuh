@@ -8,16 +8,19 @@
 // s32[oc]*s_in, and re-quantisation of the activation to u8/s8 with the static scale of the
 // output tensor.
 //
-// Arithmetic contract (oracle/slq_oracle.py `epilogue_v2` restates it exactly; fma = one rounding):
-//   per channel : wsc = wscale*s_in ; zw = zf*wsc                       (fp32 mul each)
+// Arithmetic contract (oracle/slq_oracle.py `epilogue` / `epilogue_q` restate it exactly; fma = one
+// rounding, every other op a separately rounded fp32 op):
+//   per channel : wsc = wscale*s_in ; zw = zf*wsc
+//                 fp32 out  : A = wsc        Z = zw        B = bias        sr = s_res
+//                 u8/s8 out : A = wsc*inv    Z = zw*inv    B = bias*inv    sr = s_res*inv
+//                             with inv = 1/act_scales[out_id]: the re-quantisation multiply is folded
+//                             into the per-channel constants, so an element costs 3 FMAs + converts
 //   per element : accf = f32(acc)            [two limbs: fma(f32(hi), 256, f32(lo))]
-//                 c2   = fma(f32(S), zw, bias)
-//                 y    = fma(accf, wsc, c2)
-//                 y    = fma(f32(res), s_res, y)                        (if residual)
+//                 y    = fma(accf, A, fma(f32(S), Z, B))
+//                 y    = fma(f32(res), sr, y)                           (if residual)
 //   fp32 out    : relu ? max(y, 0) : y
-//   u8 out      : cvt.rni.sat.u8(y * inv_out)      saturation at 0 IS the ReLU
-//   s8 out      : cvt.rni.sat.s8(y * inv_out)      (tensors that are not post-ReLU)
-// ~8 issue slots per element instead of ~17 for the separately-rounded form.
+//   u8 out      : sat_u8(rint(y))      saturation at 0 IS the ReLU
+//   s8 out      : sat_s8(rint(y))      (tensors that are not post-ReLU)
 #pragma once
 #include <cstdint>
 
@@ -36,16 +39,23 @@ struct EpiDev {  // device-side view of slq_epilogue (+ layer constants)
   long long M;
 };
 
-struct ChanParam {  // per output channel, staged in shared memory
+struct ChanParam {  // per output channel, staged in shared memory: (A, Z, B) of the contract above
   float wsc, zw, bias, pad;
 };
 
-__device__ __forceinline__ ChanParam make_chan_param(float wscale, float zf, float bias, float s_in) {
+// inv_out = 1/act_scales[out_id] for quantised outputs; pass quantised = false for fp32 / raw outputs
+__device__ __forceinline__ ChanParam make_chan_param(float wscale, float zf, float bias, float s_in,
+                                                     float inv_out, bool quantised) {
   ChanParam p;
   p.wsc = __fmul_rn(wscale, s_in);
   p.zw = __fmul_rn(zf, p.wsc);
   p.bias = bias;
   p.pad = 0.f;
+  if (quantised) {
+    p.wsc = __fmul_rn(p.wsc, inv_out);
+    p.zw = __fmul_rn(p.zw, inv_out);
+    p.bias = __fmul_rn(p.bias, inv_out);
+  }
   return p;
 }
 
@@ -62,15 +72,34 @@ __device__ __forceinline__ float epi_add_res(float y, uint32_t res_byte, bool re
   return __fmaf_rn(r, s_res, y);
 }
 
-__device__ __forceinline__ uint32_t epi_quant_u8(float y, float inv_s_out) {
+// y is already in units of the output scale (see the contract)
+__device__ __forceinline__ uint32_t epi_quant_u8(float y) {
   uint32_t q;
-  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q) : "f"(__fmul_rn(y, inv_s_out)));
+  asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(q) : "f"(y));
   return q;
 }
-__device__ __forceinline__ uint32_t epi_quant_s8(float y, float inv_s_out) {
+__device__ __forceinline__ uint32_t epi_quant_s8(float y) {
   int q;
-  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(__fmul_rn(y, inv_s_out)));
+  asm("cvt.rni.sat.s8.f32 %0, %1;" : "=r"(q) : "f"(y));
   return (uint32_t)q & 0xffu;
+}
+// four values -> four packed bytes: rint to s32, then two saturating pack instructions
+template <bool SIGNED>
+__device__ __forceinline__ uint32_t epi_pack4(float y0, float y1, float y2, float y3) {
+  int i0, i1, i2, i3;
+  asm("cvt.rni.s32.f32 %0, %1;" : "=r"(i0) : "f"(y0));
+  asm("cvt.rni.s32.f32 %0, %1;" : "=r"(i1) : "f"(y1));
+  asm("cvt.rni.s32.f32 %0, %1;" : "=r"(i2) : "f"(y2));
+  asm("cvt.rni.s32.f32 %0, %1;" : "=r"(i3) : "f"(y3));
+  uint32_t hi2, w;
+  if (SIGNED) {
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, 0;" : "=r"(hi2) : "r"(i3), "r"(i2));
+    asm("cvt.pack.sat.s8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(i1), "r"(i0), "r"(hi2));
+  } else {
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, 0;" : "=r"(hi2) : "r"(i3), "r"(i2));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(w) : "r"(i1), "r"(i0), "r"(hi2));
+  }
+  return w;
 }
 
 }  // namespace slq

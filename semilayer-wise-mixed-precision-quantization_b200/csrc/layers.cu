@@ -108,15 +108,20 @@ __global__ void __launch_bounds__(128) conv_simt_kernel(ConvGeom g, const uint8_
     return;
   }
   const float s_in = e.act_scales[e.in_id];
-  const ChanParam cp = make_chan_param(e.wscale[oc], e.zf[oc], e.bias[oc], s_in);
+  const bool quantised = e.out_mode != SLQ_OUT_F32;
+  const float inv = quantised ? __fdiv_rn(1.0f, e.act_scales[e.out_id]) : 1.0f;
+  const ChanParam cp = make_chan_param(e.wscale[oc], e.zf[oc], e.bias[oc], s_in, inv, quantised);
   const float Sf = (float)(int)S;
   float y = g.w16 ? epi_value<true>((int)acc_lo, (int)acc_hi, Sf, cp) : epi_value<false>((int)acc_lo, 0, Sf, cp);
-  if (e.res != nullptr) y = epi_add_res(y, e.res[m * g.Cout + oc], e.res_signed != 0, e.act_scales[e.res_id]);
+  if (e.res != nullptr) {
+    float sr = e.act_scales[e.res_id];
+    if (quantised) sr = __fmul_rn(sr, inv);
+    y = epi_add_res(y, e.res[m * g.Cout + oc], e.res_signed != 0, sr);
+  }
   if (e.out_mode == SLQ_OUT_F32) {
     reinterpret_cast<float *>(e.out)[m * g.Cout + oc] = e.relu ? fmaxf(y, 0.f) : y;
   } else {
-    const float inv = __fdiv_rn(1.0f, e.act_scales[e.out_id]);
-    const uint32_t q = e.out_mode == SLQ_OUT_S8 ? epi_quant_s8(y, inv) : epi_quant_u8(y, inv);
+    const uint32_t q = e.out_mode == SLQ_OUT_S8 ? epi_quant_s8(y) : epi_quant_u8(y);
     reinterpret_cast<uint8_t *>(e.out)[m * g.Cout + oc] = (uint8_t)q;
   }
 }
@@ -221,8 +226,8 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float *__restrict_
     *reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + pix * 64 + og * 4) = m;
   } else {
     const float inv = __fdiv_rn(1.0f, act_scales[out_id]);
-    const uint32_t q = epi_quant_u8(m.x, inv) | (epi_quant_u8(m.y, inv) << 8) |
-                       (epi_quant_u8(m.z, inv) << 16) | (epi_quant_u8(m.w, inv) << 24);
+    const uint32_t q = epi_quant_u8(__fmul_rn(m.x, inv)) | (epi_quant_u8(__fmul_rn(m.y, inv)) << 8) |
+                       (epi_quant_u8(__fmul_rn(m.z, inv)) << 16) | (epi_quant_u8(__fmul_rn(m.w, inv)) << 24);
     *reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out) + pix * 64 + og * 4) = q;
   }
 }
@@ -255,44 +260,82 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const uint8_t *__restrict_
   *reinterpret_cast<float4 *>(pooled + (long long)n * C + c4 * 4) = o;
 }
 
-// logits[n, o] = sum_c pooled[n, c] * fw[o, c] + fb[o]: 32 x 64 output tile per CTA, K chunks of 32
+// logits[n, o] = sum_c pooled[n, c] * fw[o, c] + fb[o]   (fp32 CUDA cores; fc weights stay fp32).
+// CTA = 32 images x 64 outputs, K chunks of 32 staged transposed in smem ([k][n], [k][o]) so the inner
+// loop is 2 LDS.128 + 16 FFMA; the 256 threads are two K-halves of 128 threads (4x4 outputs each)
+// whose partial sums meet in smem at the end (fixed order: deterministic).  Next chunk's global
+// loads are issued before the current chunk's math.
+constexpr int kFcBN = 32, kFcBO = 64, kFcBK = 32;
+
 __global__ void __launch_bounds__(256) fc_kernel(const float *__restrict__ pooled, int N, int C,
                                                  const float *__restrict__ fw, const float *__restrict__ fb,
                                                  int O, float *__restrict__ logits) {
-  __shared__ float As[32][33];
-  __shared__ float Bs[64][33];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> 4 outputs o, ty -> 2 images n
-  const int n0 = blockIdx.y * 32, o0 = blockIdx.x * 64;
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-      const int r = i >> 5, c = i & 31;
-      As[r][c] = (n0 + r < N && c0 + c < C) ? pooled[(long long)(n0 + r) * C + c0 + c] : 0.f;
-    }
-    for (int i = threadIdx.x; i < 64 * 32; i += 256) {
-      const int r = i >> 5, c = i & 31;
-      Bs[r][c] = (o0 + r < O && c0 + c < C) ? fw[(long long)(o0 + r) * C + c0 + c] : 0.f;
-    }
-    __syncthreads();
+  __shared__ __align__(16) float As[2][kFcBK][kFcBN + 4];
+  __shared__ __align__(16) float Bs[2][kFcBK][kFcBO + 4];
+  const int tid = threadIdx.x;
+  const int kg = tid >> 7;                 // K half of every chunk
+  const int tn = tid & 7, to = (tid >> 3) & 15;
+  const int n0 = blockIdx.y * kFcBN, o0 = blockIdx.x * kFcBO;
+  // loader mapping: one float4 (4 consecutive k) of A and two of B per thread
+  const int lr = tid >> 3, lk = (tid & 7) * 4;  // row 0..31, k offset 0..28
+  const bool a_ok = n0 + lr < N;
+  const bool b0_ok = o0 + lr < O, b1_ok = o0 + 32 + lr < O;
+  const float4 *pa = reinterpret_cast<const float4 *>(pooled + (long long)(n0 + lr) * C + lk);
+  const float4 *pb0 = reinterpret_cast<const float4 *>(fw + (long long)(o0 + lr) * C + lk);
+  const float4 *pb1 = reinterpret_cast<const float4 *>(fw + (long long)(o0 + 32 + lr) * C + lk);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 ra = a_ok ? __ldg(pa) : zero4, rb0 = b0_ok ? __ldg(pb0) : zero4, rb1 = b1_ok ? __ldg(pb1) : zero4;
+  float acc[4][4];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      const float a0 = As[ty * 2][c], a1 = As[ty * 2 + 1][c];
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int chunks = C / kFcBK;
+  for (int ch = 0; ch < chunks; ++ch) {
+    const int buf = ch & 1;
+    As[buf][lk + 0][lr] = ra.x; As[buf][lk + 1][lr] = ra.y; As[buf][lk + 2][lr] = ra.z; As[buf][lk + 3][lr] = ra.w;
+    Bs[buf][lk + 0][lr] = rb0.x; Bs[buf][lk + 1][lr] = rb0.y; Bs[buf][lk + 2][lr] = rb0.z; Bs[buf][lk + 3][lr] = rb0.w;
+    Bs[buf][lk + 0][32 + lr] = rb1.x; Bs[buf][lk + 1][32 + lr] = rb1.y;
+    Bs[buf][lk + 2][32 + lr] = rb1.z; Bs[buf][lk + 3][32 + lr] = rb1.w;
+    __syncthreads();  // one barrier per chunk: the other buffer is only rewritten after the next barrier
+    if (ch + 1 < chunks) {
+      const int adv = (ch + 1) * (kFcBK / 4);
+      ra = a_ok ? __ldg(pa + adv) : zero4;
+      rb0 = b0_ok ? __ldg(pb0 + adv) : zero4;
+      rb1 = b1_ok ? __ldg(pb1 + adv) : zero4;
+    }
+#pragma unroll
+    for (int kk = 0; kk < kFcBK / 2; ++kk) {
+      const int k = kg * (kFcBK / 2) + kk;
+      const float4 a = *reinterpret_cast<const float4 *>(&As[buf][k][tn * 4]);
+      const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][to * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+  __syncthreads();
+  float *red = &Bs[0][0][0];  // 128 threads x 16 partial sums = 2048 floats <= one Bs buffer
+  if (kg == 1) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[(i * 4 + j) * 128 + (tid & 127)] = acc[i][j];
+  }
+  __syncthreads();
+  if (kg == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int n = n0 + tn * 4 + i;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float b = Bs[tx + 16 * j][c];
-        acc[0][j] = fmaf(a0, b, acc[0][j]);
-        acc[1][j] = fmaf(a1, b, acc[1][j]);
+        const int o = o0 + to * 4 + j;
+        if (n < N && o < O) logits[(long long)n * O + o] = (acc[i][j] + red[(i * 4 + j) * 128 + tid]) + fb[o];
       }
     }
-    __syncthreads();
   }
-#pragma unroll
-  for (int i = 0; i < 2; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + ty * 2 + i, o = o0 + tx + 16 * j;
-      if (n < N && o < O) logits[(long long)n * O + o] = acc[i][j] + fb[o];
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -331,16 +374,16 @@ __global__ void __launch_bounds__(256) quantize_act_kernel(const float *__restri
     const float4 v = __ldg(y4 + i);
     uint32_t q;
     if (is_signed)
-      q = epi_quant_s8(v.x, inv) | (epi_quant_s8(v.y, inv) << 8) | (epi_quant_s8(v.z, inv) << 16) |
-          (epi_quant_s8(v.w, inv) << 24);
+      q = epi_quant_s8(__fmul_rn(v.x, inv)) | (epi_quant_s8(__fmul_rn(v.y, inv)) << 8) | (epi_quant_s8(__fmul_rn(v.z, inv)) << 16) |
+          (epi_quant_s8(__fmul_rn(v.w, inv)) << 24);
     else
-      q = epi_quant_u8(v.x, inv) | (epi_quant_u8(v.y, inv) << 8) | (epi_quant_u8(v.z, inv) << 16) |
-          (epi_quant_u8(v.w, inv) << 24);
+      q = epi_quant_u8(__fmul_rn(v.x, inv)) | (epi_quant_u8(__fmul_rn(v.y, inv)) << 8) | (epi_quant_u8(__fmul_rn(v.z, inv)) << 16) |
+          (epi_quant_u8(__fmul_rn(v.w, inv)) << 24);
     reinterpret_cast<uint32_t *>(out)[i] = q;
   }
   if (blockIdx.x == 0)
     for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x)
-      out[i] = (uint8_t)(is_signed ? epi_quant_s8(y[i], inv) : epi_quant_u8(y[i], inv));
+      out[i] = (uint8_t)(is_signed ? epi_quant_s8(__fmul_rn(y[i], inv)) : epi_quant_u8(__fmul_rn(y[i], inv)));
 }
 
 }  // namespace slq
@@ -388,12 +431,12 @@ extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t
                                 const float *fc_b, int32_t O, float *pooled, float *logits,
                                 void *stream) {
   SLQ_CHECK_ARG(x && act_scales && fc_w && fc_b && pooled && logits, "slq_tail_forward: null pointer argument");
-  SLQ_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C % 4 == 0 && O > 0, "slq_tail_forward: bad shape");
+  SLQ_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C % 32 == 0 && O > 0, "slq_tail_forward: bad shape (C must be a multiple of 32)");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 g1((unsigned)ceil_div(C / 4, 256), (unsigned)N);
   avgpool_kernel<<<g1, 256, 0, st>>>(x, HW, C, act_scales, in_id, pooled);
   SLQ_LAUNCH_CHECK();
-  dim3 g2((unsigned)ceil_div(O, 64), (unsigned)ceil_div(N, 32));
+  dim3 g2((unsigned)ceil_div(O, kFcBO), (unsigned)ceil_div(N, kFcBN));
   fc_kernel<<<g2, 256, 0, st>>>(pooled, N, C, fc_w, fc_b, O, logits);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;

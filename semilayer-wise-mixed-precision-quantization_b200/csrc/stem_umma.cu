@@ -206,8 +206,8 @@ stem_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t pk[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            pk[j] = epi_quant_u8(y[4 * j], inv_out) | (epi_quant_u8(y[4 * j + 1], inv_out) << 8) |
-                    (epi_quant_u8(y[4 * j + 2], inv_out) << 16) | (epi_quant_u8(y[4 * j + 3], inv_out) << 24);
+            pk[j] = epi_quant_u8(__fmul_rn(y[4 * j], inv_out)) | (epi_quant_u8(__fmul_rn(y[4 * j + 1], inv_out)) << 8) |
+                    (epi_quant_u8(__fmul_rn(y[4 * j + 2], inv_out)) << 16) | (epi_quant_u8(__fmul_rn(y[4 * j + 3], inv_out)) << 24);
           uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) + pix * 64 + ch * 32);
           o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);

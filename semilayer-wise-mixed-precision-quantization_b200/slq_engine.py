@@ -103,6 +103,20 @@ class Engine:
         with torch.cuda.device(device):
             self._plan()
 
+    @classmethod
+    def for_module(cls, net, x, **kw):
+        """Engine for ANY module tree shaped like the reference's ResNet (resnet.py:121-202), e.g. the
+        reference's own class patched per INTEGRATION.md B.2: cached on the module, re-packed and
+        re-calibrated on first use (call ``net._slq_engine = None`` after mutating weights)."""
+        key = (tuple(x.shape), x.device.index)
+        cached = getattr(net, "_slq_engine", None)
+        if cached is None or cached[0] != key:
+            eng = cls(net, x.shape[0], x.shape[2], x.shape[3], x.device, **kw)
+            eng.refresh_weights()
+            eng.calibrate(x)
+            net._slq_engine = cached = (key, eng)
+        return cached[1]
+
     # ------------------------------------------------------------------------------------------
     def _new_act(self, shape_nhwc, signed=False):
         self.act.append(torch.empty(shape_nhwc, dtype=torch.uint8, device=self.device))

@@ -147,13 +147,12 @@ class ConvCase:
 def oracle_epilogue_case(case, wscale, zf, bias, scales, in_id, out_id, res, res_id, res_signed, relu, mode):
     import slq_lib as L
     lo, hi, S = case.oracle_acc()
-    y = so.epilogue(lo, S, zf, wscale, bias, scales[in_id], res, scales[res_id] if res is not None else None,
-                    relu=bool(relu) and mode == L.OUT_F32, acc_hi=hi, res_signed=bool(res_signed))
+    s_res = scales[res_id] if res is not None else None
     if mode == L.OUT_F32:
-        return y
-    if mode == L.OUT_S8:
-        return so.requant_s8(y, scales[out_id])
-    return so.requant_u8(y, scales[out_id])
+        return so.epilogue(lo, S, zf, wscale, bias, scales[in_id], res, s_res, relu=bool(relu), acc_hi=hi,
+                           res_signed=bool(res_signed))
+    return so.epilogue_q(lo, S, zf, wscale, bias, scales[in_id], scales[out_id], res, s_res, acc_hi=hi,
+                         res_signed=bool(res_signed), signed_out=(mode == L.OUT_S8))
 
 
 def rel_l2(a, b):

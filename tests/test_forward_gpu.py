@@ -82,8 +82,8 @@ def test_activation_pipeline_matches_numpy_oracle_first_block():
     meta = [so.encode_row(w[oc]) for oc in range(op.Cout)]
     codes = np.stack([m[1].reshape(op.Cin, op.k, op.k).transpose(1, 2, 0) for m in meta]).astype(np.int64)
     acc, S, _, _ = so.conv_acc(xin, codes, op.stride, op.pad)
-    y = so.epilogue(acc, S, op.zf.cpu().numpy(), op.wscale.cpu().numpy(), op.bias.cpu().numpy(), scales[op.in_id])
-    want = so.requant_u8(y, scales[op.out_id]).reshape(eng.act[op.out_id].shape)
+    want = so.epilogue_q(acc, S, op.zf.cpu().numpy(), op.wscale.cpu().numpy(), op.bias.cpu().numpy(),
+                         scales[op.in_id], scales[op.out_id]).reshape(eng.act[op.out_id].shape)
     assert np.array_equal(eng.act[op.out_id].cpu().numpy(), want)
     # stem: fp32 conv + bn + relu + maxpool against torch, then the same quantiser
     import torch.nn.functional as F
@@ -92,7 +92,8 @@ def test_activation_pipeline_matches_numpy_oracle_first_block():
         t = F.relu(F.batch_norm(t, net.bn1.running_mean, net.bn1.running_var, net.bn1.weight, net.bn1.bias, False, 0.0, net.bn1.eps))
         t = F.max_pool2d(t, 3, 2, 1).permute(0, 2, 3, 1).contiguous().cpu().numpy()
     s0 = scales[0]
-    assert abs(float(t.max()) / 255.0 - float(s0)) <= 1e-5 * float(s0) + 1e-9
+    # the stem runs fp16 operands on the tensor core (fp32 accumulation): ~3e-4 relative
+    assert abs(float(t.max()) / 255.0 - float(s0)) <= 1e-3 * float(s0) + 1e-9
     q = so.requant_u8(t, s0)
     got = eng.act[0].cpu().numpy().astype(np.int32)
     assert np.abs(got - q.astype(np.int32)).max() <= 1  # fp16 tensor-core operands / summation order
