@@ -162,6 +162,12 @@ typedef struct slq_epilogue {
   int32_t relu;
 } slq_epilogue;
 
+/* Debug timeline: when buf != NULL, CTA 0 of every later slq_conv_launch logs (event+1, index, SM clock)
+ * triples into buf (3*capacity_events int64, zeroed by the caller; 24 issuers own capacity/24 slots
+ * each).  Events: 0/1 A load issue begin/end, 2/3 B load issue begin/end, 4 MMA saw K block, 5/6
+ * epilogue tile begin/end.  NULL switches tracing off.  Not for production use.                    */
+SLQ_API int slq_debug_set_trace(int64_t *buf, int32_t capacity_events);
+
 /* y[m, oc] = (acc[m,oc] + z[oc] * S[m]) * wscale[oc] * act_scales[in_id] + bias[oc]
  *            (+ res[m,oc] * act_scales[res_id]) ; ReLU ; u8 = clamp(rint(y / act_scales[out_id])) */
 SLQ_API int slq_conv_launch(slq_conv *c, const slq_epilogue *e, void *stream);

@@ -34,31 +34,130 @@ constexpr int kThreads = 640;
 constexpr int kTeam = 256;  // threads of one epilogue team
 constexpr int kOutTileBytes = kTileM * 128;  // u8 output / residual staging tile (128 rows x <=128 B)
 
-template <int SWZ>
-struct Cfg {
-  static constexpr int kStages = (SWZ == 128) ? 4 : 6;
-  static constexpr int kABytes = kTileM * SWZ;
-  static constexpr int kBRows = 128 + 16;  // bn_cols (<=128) + 16 rows for the ones-row group
-  static constexpr int kBBytes = kBRows * SWZ;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kPipeBytes = kStages * kStageBytes;
-  static constexpr int kOutOff = kPipeBytes;                      // 2 output staging tiles
-  static constexpr int kResOff = kOutOff + 2 * kOutTileBytes;     // 2 residual tiles
-  static constexpr int kPrmOff = kResOff + 2 * kOutTileBytes;     // 2 x 128 ChanParam
-  static constexpr int kBarOff = kPrmOff + 2 * 128 * 16;
-  static constexpr int kSmemBytes = 1024 + kBarOff + 256;
-  static_assert(kStageBytes % 1024 == 0, "stage must keep 1024B alignment");
-  static_assert(kSmemBytes <= 232448, "exceeds 227 KB of shared memory");
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 232448;  // 227 KB: the most dynamic shared memory one CTA may own
+
+// Shared-memory carve-up of one layer (byte offsets from the 1024-aligned base), decided on the host.
+//   streamed B : every pipeline stage holds {A tile, B tile}; B is re-fetched for every tile.
+//   resident B : the n-tile's whole weight matrix (num_kb B tiles) stays in smem for all the M tiles a
+//                CTA works on, stages hold A only.  The TMA engine moves ~one (<=128-byte) smem row
+//                per ~4 cycles per SM, so not re-sending bn+16 weight rows per K block cuts the rows
+//                per tile by 1.3-1.9x on the small-K layers.
+struct SmemPlan {
+  int stages;        // A (or A+B) pipeline depth
+  int stage_bytes;   // stride between stages
+  int a_bytes;       // kTileM * SWZ
+  int b_tile_bytes;  // (bn_cols + 16) * SWZ
+  int b_resident;    // 1: B tiles at b_off + kb * b_tile_bytes ; 0: inside each stage after A
+  int b_off;
+  int res_bufs;      // depth of the residual (block identity) prefetch ring, 0 without residual
+  int out_off, res_off, prm_off, bar_off;
+  int total;         // dynamic smem bytes to request (including 1024 B of alignment slack)
 };
+
+constexpr int kMaxResBufs = 4;
+
+inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
+  SmemPlan p{};
+  p.a_bytes = kTileM * swz;
+  p.b_tile_bytes = (g.bn_cols + 16) * swz;
+  p.res_bufs = has_res ? kMaxResBufs : 0;
+  const int num_kb = g.Ktot / swz;
+  // out staging (2), residual ring, prm, barriers, alignment slack
+  const int fixed = (2 + p.res_bufs) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
+  const int avail = kSmemLimit - fixed;
+  const long long b_all = (long long)num_kb * p.b_tile_bytes;
+  if (b_all + 3LL * p.a_bytes <= avail) {
+    p.b_resident = 1;
+    p.stage_bytes = p.a_bytes;
+    p.stages = (int)std::min<long long>(kMaxStages, (avail - b_all) / p.a_bytes);
+  } else {
+    p.b_resident = 0;
+    p.stage_bytes = p.a_bytes + p.b_tile_bytes;
+    p.stages = std::min(kMaxStages, avail / p.stage_bytes);
+  }
+  p.b_off = p.stages * p.stage_bytes;
+  p.out_off = p.b_off + (p.b_resident ? (int)b_all : 0);
+  p.res_off = p.out_off + 2 * kOutTileBytes;
+  p.prm_off = p.res_off + p.res_bufs * kOutTileBytes;
+  p.bar_off = p.prm_off + 2 * 128 * 16;
+  p.total = 1024 + p.bar_off + 512;
+  return p;
+}
+
+// CTAs to launch: one per SM; with resident weights every CTA keeps ONE n-tile for its whole life, so
+// the grid is the largest multiple of n_tiles that fits (148 -> 144 for 8 or 16 n-tiles).
+inline int plan_grid(const ConvGeom &g, const SmemPlan &p, int sms) {
+  const long long m_tiles = (g.M + kTileM - 1) / kTileM;
+  if (p.b_resident) {
+    const int per_n = (int)std::min<long long>(std::max(sms / g.n_tiles, 1), m_tiles);
+    return per_n * g.n_tiles;
+  }
+  return (int)std::min<long long>(m_tiles * g.n_tiles, sms);
+}
 
 struct KernelArgs {
   ConvGeom g;
   EpiDev e;
+  SmemPlan sp;
   int a_im2col;
   int num_kb;          // K blocks per tile = kh*kw*Cin / SWZ
   int chunks_per_tap;  // Cin / SWZ
   int tma_out;         // 1: u8/s8 output through the smem tile + TMA store
+  int prod_lanes;      // lanes of warp 0 that issue TMA loads (one thread sustains only ~1 box / 700 clk)
+  int res_lanes;       // lanes of warp 3 that issue residual loads
   long long m_tiles;
+  long long *trace;    // debug: CTA 0 logs (event, index, clock) triples here (slq_debug_set_trace)
+  int trace_cap;
+};
+
+// debug timeline (CTA 0 only): every issuer owns a private region of the buffer, so logging is one
+// fire-and-forget store (no atomics: their latency would distort the very thing being measured)
+constexpr int kTraceIssuers = 24;
+__device__ __forceinline__ void trace_ev(const KernelArgs &a, int issuer, int &n, int ev, int idx) {
+  if (a.trace == nullptr || blockIdx.x != 0) return;
+  const int per = a.trace_cap / kTraceIssuers;
+  if (n < per) {
+    long long *p = a.trace + 3LL * (issuer * per + n);
+    p[0] = ev + 1;  // 0 = empty slot
+    p[1] = idx;
+    p[2] = clock64();
+    ++n;
+  }
+}
+
+// The tiles one CTA works on, in the order every role walks them.  Both orders are m-major in time
+// (CTAs that run together touch neighbouring pixels: A tiles are shared through L2 and the channel
+// slices of an output row are written close together).
+//   streamed B : tile = blockIdx + i*grid over (m_tile, n_tile) pairs
+//   resident B : n_tile = blockIdx % n_tiles for the CTA's whole life, m_tile strided
+struct TileWalk {  // everything fits 32 bits (M <= 2^31): no 64-bit divisions on the issue paths
+  int count, first_m, step_m;
+  int first, step;
+  int n_tiles, fixed_n, my_n;
+  __device__ TileWalk(const KernelArgs &a) {
+    n_tiles = a.g.n_tiles;
+    fixed_n = a.sp.b_resident;
+    const int m_tiles = (int)a.m_tiles;
+    if (fixed_n) {
+      const int per_n = (int)gridDim.x / n_tiles;
+      my_n = (int)blockIdx.x % n_tiles;
+      first_m = (int)blockIdx.x / n_tiles;
+      step_m = per_n;
+      count = first_m < m_tiles ? (m_tiles - first_m + per_n - 1) / per_n : 0;
+      first = step = 0;
+    } else {
+      const int total = m_tiles * n_tiles;
+      first = (int)blockIdx.x;
+      step = (int)gridDim.x;
+      count = first < total ? (total - first + step - 1) / step : 0;
+      my_n = 0; first_m = step_m = 0;
+    }
+  }
+  __device__ void at(int i, int &m_tile, int &n_tile) const {
+    if (fixed_n) { n_tile = my_n; m_tile = first_m + i * step_m; }
+    else { const int t = first + i * step; m_tile = t / n_tiles; n_tile = t - m_tile * n_tiles; }
+  }
 };
 
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
@@ -79,27 +178,29 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmR,
                  const KernelArgs a) {
-  using C = Cfg<SWZ>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + C::kBarOff;
+  const SmemPlan &sp = a.sp;
+  const uint32_t bar_base = smem_base + sp.bar_off;
   // barrier slots (8 bytes each)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 2 + b); };
-  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 4 + b); };
-  auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * C::kStages + 6 + b); };
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + C::kBarOff + 8 * (2 * C::kStages + 8));
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + b); };
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 2 + b); };
+  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 4 + b); };
+  auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 4 + kMaxResBufs + b); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * kMaxStages + 4 + 2 * kMaxResBufs);  // resident B landed
+  volatile uint32_t *tmem_slot =
+      reinterpret_cast<volatile uint32_t *>(smem + sp.bar_off + 8 * (2 * kMaxStages + 5 + 2 * kMaxResBufs));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom &g = a.g;
   const EpiDev &e = a.e;
   const int bn_cols = g.bn_cols;
   const int umma_n = bn_cols + 16;
-  const long long total_tiles = a.m_tiles * g.n_tiles;
   const bool has_res = RES == kResDyn ? (e.res != nullptr) : (RES != kResNone);
+  const TileWalk walk(a);
 
   // ---- one-time setup -----------------------------------------------------------------------
   if (warp == 0 && lane == 0) {
@@ -109,16 +210,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (has_res) prefetch_tmap(&tmR);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < C::kStages; ++s) {
+    for (int s = 0; s < sp.stages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tfull_bar(b), 1);
       mbar_init(tempty_bar(b), kTeam);
+    }
+    for (int b = 0; b < sp.res_bufs; ++b) {
       mbar_init(rfull_bar(b), 1);
       mbar_init(rempty_bar(b), kTeam);
     }
+    mbar_init(bfull_bar, 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -128,14 +232,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // constant "ones" row group behind the TMA-written B rows of every stage:
+  // constant "ones" row group behind the TMA-written B rows of every B tile:
   // row bn_cols = 0x01.., rows bn_cols+1 .. +15 = 0  (identical bytes are swizzle-invariant)
-  for (int i = threadIdx.x; i < C::kStages * 16 * (SWZ / 16); i += blockDim.x) {
-    const int s = i / (16 * (SWZ / 16));
-    const int rem = i % (16 * (SWZ / 16));
-    const int row = rem / (SWZ / 16), chunk = rem % (SWZ / 16);
-    uint4 v = row == 0 ? make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u) : make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4 *>(smem + s * C::kStageBytes + C::kABytes + (bn_cols + row) * SWZ + chunk * 16) = v;
+  {
+    const int b_tiles = sp.b_resident ? a.num_kb : sp.stages;
+    const int b_stride = sp.b_resident ? sp.b_tile_bytes : sp.stage_bytes;
+    const int b_first = sp.b_resident ? sp.b_off : sp.a_bytes;
+    for (int i = threadIdx.x; i < b_tiles * 16 * (SWZ / 16); i += blockDim.x) {
+      const int t = i / (16 * (SWZ / 16));
+      const int rem = i % (16 * (SWZ / 16));
+      const int row = rem / (SWZ / 16), chunk = rem % (SWZ / 16);
+      uint4 v = row == 0 ? make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4 *>(smem + b_first + t * b_stride + (bn_cols + row) * SWZ + chunk * 16) = v;
+    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -143,83 +252,138 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ================================ TMA producer ============================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)(C::kABytes + bn_cols * SWZ);
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const long long m_tile = tile / g.n_tiles;
-        const int n_tile = (int)(tile % g.n_tiles);
-        const long long m0 = m_tile * kTileM;
-        int cw = 0, chh = 0, cn = 0;
-        if (a.a_im2col) {
-          const int q = (int)(m0 % g.Wo);
-          const int p = (int)((m0 / g.Wo) % g.Ho);
-          cn = (int)(m0 / ((long long)g.Wo * g.Ho));
-          cw = q * g.stride - g.pad;
-          chh = p * g.stride - g.pad;
-        }
-        for (int kb = 0; kb < a.num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          const uint32_t sb = sa + C::kABytes;
-          mbar_expect_tx(full_bar(stage), tx_bytes);
-          const int tap = kb / a.chunks_per_tap;
-          const int cchunk = kb - tap * a.chunks_per_tap;
-          if (a.a_im2col) {
-            const int r = tap / g.kw, s = tap - r * g.kw;
-            tma_load_im2col_4d(sa, &tmA, full_bar(stage), cchunk * SWZ, cw, chh, cn, (uint16_t)s, (uint16_t)r);
-          } else {
-            tma_load_2d(sa, &tmA, full_bar(stage), cchunk * SWZ, (int)m0);
+  // ================================ TMA producers ===============================================
+  // Issuing one TMA box costs the issuing WARP ~250 (tiled) to ~420 (im2col) cycles and the lanes of a
+  // warp take turns (timeline: tools/trace_conv.py), so a single producer warp caps a K block at
+  // ~700-1300 cycles -- 2-4x the tensor time.  The loads are therefore spread over the three warps
+  // that have nothing else to do (0, 2 = TMEM allocator, 3):
+  //   A tiles   : warp 0, plus warp 2 when the weights are resident, plus warp 3 when there is no residual
+  //   B tiles   : warp 2 when weights are streamed (resident weights land once, issued by warp 0)
+  //   residual  : warp 3
+  // K blocks are dealt round-robin over (A warps x prod_lanes) issuers; each fills "its" stages and the
+  // MMA warp consumes them in order.
+  const int n_a_warps = 1 + (sp.b_resident ? 1 : 0) + (has_res ? 0 : 1);
+  int a_idx = -1;  // this warp's index among the A-producer warps
+  if (warp == 0) a_idx = 0;
+  else if (warp == 2 && sp.b_resident) a_idx = 1;
+  else if (warp == 3 && !has_res) a_idx = sp.b_resident ? 2 : 1;
+  const bool b_warp = warp == 2 && !sp.b_resident;
+  if (warp != 1 && warp < 4 && (a_idx >= 0 || b_warp)) {
+    const int L = a.prod_lanes;
+    if (lane < L) {
+      const uint32_t b_bytes = (uint32_t)(bn_cols * SWZ);
+      const uint32_t tx_bytes = (uint32_t)sp.a_bytes + (sp.b_resident ? 0u : b_bytes);
+      if (warp == 0 && sp.b_resident && walk.count > 0) {  // this CTA's n-tile never changes
+        if (lane == 0) mbar_expect_tx(bfull_bar, b_bytes * (uint32_t)a.num_kb);
+        for (int kb = lane; kb < a.num_kb; kb += L)
+          tma_load_2d(smem_base + sp.b_off + kb * sp.b_tile_bytes, &tmB, bfull_bar, kb * SWZ, walk.my_n * bn_cols);
+      }
+      const int items = walk.count * a.num_kb;
+      int tn = 0;
+      const int tid_ = (b_warp ? 12 : a_idx * 4) + lane;
+      const int first = b_warp ? lane : a_idx + n_a_warps * lane;
+      const int step = b_warp ? L : n_a_warps * L;
+      // (i, kb) and the stage/phase advance incrementally; tile coordinates only when i changes
+      int i = first / a.num_kb, kb = first - i * a.num_kb;
+      int stage = first % sp.stages;
+      uint32_t phase = (uint32_t)((first / sp.stages) & 1);
+      const int step_i = step / a.num_kb, step_kb = step - step_i * a.num_kb;
+      const int step_st = step % sp.stages, step_ph = step / sp.stages;
+      int cur_i = -1, n_tile = 0, m0 = 0, cw = 0, chh = 0, cn = 0;
+      for (int c = first; c < items; c += step) {
+        if (i != cur_i) {
+          int m_tile;
+          walk.at(i, m_tile, n_tile);
+          m0 = m_tile * kTileM;
+          if (a.a_im2col && !b_warp) {
+            const int hw = g.Wo * g.Ho;
+            cn = m0 / hw;
+            const int rem = m0 - cn * hw;
+            const int p = rem / g.Wo;
+            cw = (rem - p * g.Wo) * g.stride - g.pad;
+            chh = p * g.stride - g.pad;
           }
-          tma_load_2d(sb, &tmB, full_bar(stage), kb * SWZ, n_tile * bn_cols);
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          cur_i = i;
         }
+        const uint32_t sa = smem_base + stage * sp.stage_bytes;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (b_warp) {  // the A issuer posts the stage's byte count; tx-count may run negative meanwhile
+          trace_ev(a, tid_, tn, 2, c);
+          tma_load_2d(sa + sp.a_bytes, &tmB, full_bar(stage), kb * SWZ, n_tile * bn_cols);
+          trace_ev(a, tid_, tn, 3, c);
+        } else {
+          trace_ev(a, tid_, tn, 0, c);
+          mbar_expect_tx(full_bar(stage), tx_bytes);
+          if (a.a_im2col) {
+            const int tap = kb / a.chunks_per_tap;
+            const int cchunk = kb - tap * a.chunks_per_tap;
+            const int r = tap / g.kw, sx = tap - r * g.kw;
+            tma_load_im2col_4d(sa, &tmA, full_bar(stage), cchunk * SWZ, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
+          } else {
+            tma_load_2d(sa, &tmA, full_bar(stage), kb * SWZ, m0);
+          }
+          trace_ev(a, tid_, tn, 1, c);
+        }
+        kb += step_kb; i += step_i;
+        if (kb >= a.num_kb) { kb -= a.num_kb; ++i; }
+        stage += step_st; phase ^= (uint32_t)(step_ph & 1);
+        if (stage >= sp.stages) { stage -= sp.stages; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
-    if (lane == 0) {
-      // instruction descriptor: D=s32, A=B=u8, both K-major, M=128, N=umma_n
-      const uint32_t idesc = (2u << 4) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      long long it = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = (int)(it & 1);
-        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-        mbar_wait(tempty_bar(buf), acc_phase ^ 1);  // epilogue has drained this accumulator
+    // The WHOLE warp walks the loop (convergent, every operand warp-uniform, so the descriptors live
+    // in uniform registers) and one elected lane issues.  Issuing from inside an `if (lane == 0)`
+    // region instead makes the compiler wrap every tcgen05.mma in an ELECT/R2UR.BROADCAST loop:
+    // ~178 cycles per instruction whatever its N (tools/umma_bench.cu), i.e. 2.5x the tensor time.
+    // instruction descriptor: D=s32, A=B=u8, both K-major, M=128, N=umma_n
+    const uint32_t idesc = (2u << 4) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int tn = 0;
+    if (sp.b_resident && walk.count > 0) {
+      mbar_wait(bfull_bar, 0);  // the CTA's weights are in shared memory
+      tc_fence_after();
+    }
+    for (int i = 0; i < walk.count; ++i) {
+      const int buf = i & 1;
+      const uint32_t acc_phase = (uint32_t)((i >> 1) & 1);
+      mbar_wait(tempty_bar(buf), acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_u + buf * kAccStride;
+      for (int kb = 0; kb < a.num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * kAccStride;
-        for (int kb = 0; kb < a.num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * C::kStageBytes;
-          const uint64_t da = make_smem_desc<SWZ>(sa);
-          const uint64_t db = make_smem_desc<SWZ>(sa + C::kABytes);
+        if (a.trace != nullptr && lane == 0) trace_ev(a, 16, tn, 4, i * a.num_kb + kb);
+        const uint32_t sa = smem_base + stage * sp.stage_bytes;
+        const uint32_t sb = sp.b_resident ? smem_base + sp.b_off + kb * sp.b_tile_bytes : sa + sp.a_bytes;
+        const uint64_t da = make_smem_desc<SWZ>(sa);
+        const uint64_t db = make_smem_desc<SWZ>(sb);
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < SWZ / 32; ++k)  // UMMA_K = 32 bytes of K per instruction
             umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
           umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (kb == a.num_kb - 1) umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
         }
-        umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == sp.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 3) {
-    // ================================ residual producer =======================================
-    if (lane == 0 && has_res) {
+    // ================================ residual producer (has_res: warp 3 is not an A warp) ====
+    if (has_res && lane < a.res_lanes) {
       const uint32_t res_bytes = (uint32_t)(kTileM * g.bn_ch);
-      long long it = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = (int)(it & 1);
-        const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      for (int it = lane; it < walk.count; it += a.res_lanes) {
+        int m_tile, n_tile;
+        walk.at(it, m_tile, n_tile);
+        const int buf = (int)(it % sp.res_bufs);
+        const uint32_t ph = (uint32_t)((it / sp.res_bufs) & 1);
         mbar_wait(rempty_bar(buf), ph ^ 1);
         mbar_expect_tx(rfull_bar(buf), res_bytes);
-        tma_load_2d(smem_base + C::kResOff + buf * kOutTileBytes, &tmR, rfull_bar(buf),
-                    (int)(tile % g.n_tiles) * g.bn_ch, (int)((tile / g.n_tiles) * kTileM));
+        tma_load_2d(smem_base + sp.res_off + buf * kOutTileBytes, &tmR, rfull_bar(buf), n_tile * g.bn_ch,
+                    (int)(m_tile * kTileM));
       }
     }
   } else if (warp >= 4) {
@@ -231,10 +395,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int wq = warp & 3;                       // TMEM lane quarter this warp may touch
     const int et = threadIdx.x - 128 - team * kTeam;  // 0..255 inside the team
     const int row = wq * 32 + lane;                // tile row == TMEM lane
-    ChanParam *prm = reinterpret_cast<ChanParam *>(smem + C::kPrmOff) + team * 128;
-    const uint32_t prm_s = smem_base + C::kPrmOff + team * 128 * 16;
-    const uint32_t stg = smem_base + C::kOutOff + team * kOutTileBytes;
-    const uint32_t rsb = smem_base + C::kResOff + team * kOutTileBytes;
+    ChanParam *prm = reinterpret_cast<ChanParam *>(smem + sp.prm_off) + team * 128;
+    const uint32_t prm_s = smem_base + sp.prm_off + team * 128 * 16;
+    const uint32_t stg = smem_base + sp.out_off + team * kOutTileBytes;
     float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
     if (OUT != SLQ_OUT_ACC) {
       s_in = e.act_scales[e.in_id];
@@ -245,11 +408,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int units = g.bn_ch / CW;
     const int u0 = half * (units >> 1), u1 = u0 + (units >> 1);
     int last_n_tile = -1;
-    long long it = team;
-    for (long long tile = blockIdx.x + (long long)team * gridDim.x; tile < total_tiles;
-         tile += 2LL * gridDim.x, it += 2) {
-      const long long m_tile = tile / g.n_tiles;
-      const int n_tile = (int)(tile % g.n_tiles);
+    int tn = 0;
+    for (int it = team; it < walk.count; it += 2) {
+      int m_tile, n_tile;
+      walk.at(it, m_tile, n_tile);
       const uint32_t ph = (uint32_t)((it >> 1) & 1);
       // staging tile free again? (the previous TMA store of this team has read it)
       if (a.tma_out && et == 0) tma_store_wait_read();
@@ -266,9 +428,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       mbar_wait(tfull_bar(team), ph);
       tc_fence_after();
-      if (has_res) mbar_wait(rfull_bar(team), ph);
+      if (a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 5, (int)it);
+      const int rbuf = has_res ? (int)(it % sp.res_bufs) : 0;
+      const uint32_t rsb = smem_base + sp.res_off + rbuf * kOutTileBytes;
+      if (has_res) mbar_wait(rfull_bar(rbuf), (uint32_t)((it / sp.res_bufs) & 1));
       const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + team * kAccStride;
-      const long long m = m_tile * kTileM + row;
+      const long long m = (long long)m_tile * kTileM + row;
       const bool valid = m < g.M;
       const uint32_t S_raw = tmem_ld1(trow + bn_cols);
       tmem_ld_wait();
@@ -337,8 +502,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
+      if (a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
       mbar_arrive(tempty_bar(team));  // kTeam arrivals release the accumulator buffer
-      if (has_res) mbar_arrive(rempty_bar(team));
+      if (has_res) mbar_arrive(rempty_bar(rbuf));
       if (a.tma_out) {
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + team, kTeam);
@@ -475,25 +641,37 @@ static int build_tensor_maps(slq_conv *c) {
   return SLQ_OK;
 }
 
+static long long *g_trace = nullptr;  // slq_debug_set_trace
+static int g_trace_cap = 0;
+
 template <int SWZ, bool W16, int OUT, int RES>
 static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {
-  using C = Cfg<SWZ>;
   static bool attr_done = false;
   if (!attr_done) {
     SLQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<SWZ, W16, OUT, RES>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_done = true;
   }
   KernelArgs a;
   a.g = c->g;
   a.e = e;
+  a.sp = make_plan(c->g, SWZ, e.res != nullptr);
+  const int grid = plan_grid(c->g, a.sp, sm_count());
+  // An issuing lane may run at most ONE mbarrier phase ahead of the consumer (parity waits alias two
+  // phases apart): lanes <= pipeline depth guarantees it (a lane's previous item is < depth behind).
+  {
+    const int a_warps = 1 + (a.sp.b_resident ? 1 : 0) + (e.res == nullptr ? 1 : 0);
+    a.prod_lanes = std::max(1, std::min(4, a.sp.stages / a_warps));  // a_warps * lanes <= stages
+  }
+  a.res_lanes = std::min(2, std::max(a.sp.res_bufs, 1));
+  a.trace = g_trace;
+  a.trace_cap = g_trace_cap;
   a.a_im2col = c->a_im2col;
   a.chunks_per_tap = c->g.Cin / SWZ;
   a.num_kb = c->g.kh * c->g.kw * a.chunks_per_tap;
   a.m_tiles = ceil_div(c->g.M, kTileM);
   a.tma_out = tma_out;
-  conv_umma_kernel<SWZ, W16, OUT, RES><<<c->num_ctas, kThreads, C::kSmemBytes, st>>>(c->tmA, c->tmB, c->tmO,
-                                                                                   c->tmR, a);
+  conv_umma_kernel<SWZ, W16, OUT, RES><<<grid, kThreads, a.sp.total, st>>>(c->tmA, c->tmB, c->tmO, c->tmR, a);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }
@@ -533,6 +711,11 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
   SLQ_CHECK_ARG(c != nullptr, "slq_conv_create: out of host memory");
   c->desc = *d;
   c->g = make_geom(*d);
+  if (c->g.M > 0x7fff0000LL) {
+    delete c;
+    set_error("slq_conv_create: more than 2^31 output pixels");
+    return SLQ_ERR_UNSUPPORTED;
+  }
   c->in = in;
   c->wg = wg;
   c->swizzle = (d->Cin % 128 == 0) ? 128 : 64;
@@ -560,13 +743,19 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
     c->tmR = c->tmB;
     const long long tiles = ceil_div(c->g.M, kTileM) * c->g.n_tiles;
     c->num_ctas = (int)std::min<long long>(tiles, sm_count());
-    c->smem_bytes = c->swizzle == 128 ? Cfg<128>::kSmemBytes : Cfg<64>::kSmemBytes;
+    c->smem_bytes = make_plan(c->g, c->swizzle, true).total;
   }
   *out = c;
   return SLQ_OK;
 }
 
 extern "C" void slq_conv_destroy(slq_conv *c) { delete c; }
+
+extern "C" int slq_debug_set_trace(int64_t *buf, int32_t capacity_events) {
+  g_trace = reinterpret_cast<long long *>(buf);
+  g_trace_cap = buf ? capacity_events : 0;
+  return SLQ_OK;
+}
 
 extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream) {
   SLQ_CHECK_ARG(c && ep, "slq_conv_launch: null handle/epilogue");

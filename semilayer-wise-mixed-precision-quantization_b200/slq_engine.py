@@ -251,8 +251,9 @@ class Engine:
 
     def calibrate(self, x):
         """One pass with fp32 layer outputs: every activation tensor's static scale becomes
-        absmax/255 (u8) or absmax/127 (s8) of this batch; tensors are then re-quantised so that
-        the pass also leaves the same bytes in HBM that forward(x) will produce."""
+        absmax/255 (u8) or absmax/127 (s8) of this batch.  Each layer is then launched again in its
+        quantised output mode, so the pass leaves exactly the bytes in HBM that forward(x) produces
+        (and every later layer is calibrated on what it will really see)."""
         lib = self.lib
         x = self._check_x(x)
         with torch.cuda.device(self.device):
@@ -261,13 +262,14 @@ class Engine:
             n0 = self.act[0].numel()
             self._stem(x.data_ptr(), f32.data_ptr(), L.OUT_F32, st)
             L.check(lib.slq_absmax_scale(f32.data_ptr(), n0, sc, 0, 255, tmp, st))
-            L.check(lib.slq_quantize_act(f32.data_ptr(), n0, sc, 0, 0, self.act[0].data_ptr(), st))
+            self._stem(x.data_ptr(), self.act[0].data_ptr(), L.OUT_U8, st)
             for op in self.ops:
                 n = op.M * op.Cout
                 L.check(lib.slq_conv_launch(op.handle, ctypes.byref(self._epilogue(op, L.OUT_F32, f32.data_ptr())), st))
                 L.check(lib.slq_absmax_scale(f32.data_ptr(), n, sc, op.out_id, 127 if op.signed else 255, tmp, st))
-                L.check(lib.slq_quantize_act(f32.data_ptr(), n, sc, op.out_id, 1 if op.signed else 0,
-                                             self.act[op.out_id].data_ptr(), st))
+                mode = L.OUT_S8 if op.signed else L.OUT_U8
+                e = self._epilogue(op, mode, self.act[op.out_id].data_ptr())
+                L.check(lib.slq_conv_launch(op.handle, ctypes.byref(e), st))
         self.calibrated = True
 
     def forward(self, x):

@@ -47,6 +47,7 @@ SIGNATURES = {
     "slq_conv_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, ctypes.POINTER(_vp)]),
     "slq_conv_destroy": (None, [_vp]),
     "slq_conv_launch": (ctypes.c_int, [_vp, ctypes.POINTER(Epilogue), _vp]),
+    "slq_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
     "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
     "slq_stem_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "slq_stem_create": (ctypes.c_int, [_i32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),

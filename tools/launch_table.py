@@ -1,20 +1,22 @@
-"""tools/launch_table.py -- prints an `ncu --metrics gpu__time_duration.sum --csv` launch list."""
+"""tools/launch_table.py -- per-launch device times of an `ncu --metrics gpu__time_duration.sum --csv`
+launch list, one line per launch, plus the sum (cold-cache, serialised: compare shares)."""
 import csv
 import sys
 
-rows = list(csv.reader(open(sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/launches.csv")))
-hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
-hdr = rows[hi]
-ni, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-tot, by = 0.0, {}
-for r in rows[hi + 1:]:
-    if len(r) < len(hdr):
-        continue
-    t = float(r[vi].replace(",", "")) / 1e3
-    name = r[ni].split("(")[0][-34:]
-    tot += t
-    by[name] = by.get(name, 0) + t
-    print("%3s %-36s %9.1f us" % (r[0], name, t))
-print("total %.1f us" % tot)
-for k, v in sorted(by.items(), key=lambda kv: -kv[1]):
-    print("  %-36s %9.1f us  %5.1f%%" % (k, v, 100 * v / tot))
+
+def load(path):
+    rows = list(csv.reader(open(path, newline="")))
+    hi = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
+    out = []
+    for r in rows[hi + 1:]:
+        name = r[4].split("(")[0].replace("void slq::", "").replace("void ", "")
+        out.append((name, r[8], float(r[-1]) / 1000.0))
+    return out
+
+
+if __name__ == "__main__":
+    cols = [load(p) for p in sys.argv[1:]]
+    for i, (name, grid, t) in enumerate(cols[0]):
+        extra = "".join("  %8.1f" % c[i][2] if i < len(c) else "" for c in cols[1:])
+        print("%3d %-40s %-14s %8.1f%s" % (i, name[:40], grid, t, extra))
+    print("sum", " ".join("%.1f" % sum(t for _, _, t in c) for c in cols))
