@@ -339,10 +339,22 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // instruction descriptor: D=s32, A=B=u8, both K-major, M=128, N=umma_n
     const uint32_t idesc = (2u << 4) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    int stage = 0;
-    uint32_t phase = 0;
+    // This warp's own instruction stream is what paces the small-K layers (one warp retires a
+    // dependent instruction every ~5 cycles), so everything that can be is carried incrementally:
+    // descriptor low words (smem address >> 4) per stage / resident B tile, barrier addresses, phase.
+    const uint64_t desc_hi = make_smem_desc<SWZ>(0) & 0xffffffff00000000ull;
+    const uint32_t desc_lo0 = (uint32_t)(make_smem_desc<SWZ>(0) & 0xffffffffull);  // flags of the low word
+    const uint32_t n_stages = (uint32_t)sp.stages, n_kb = (uint32_t)a.num_kb;
+    const uint32_t stage16 = (uint32_t)sp.stage_bytes >> 4, a16 = (uint32_t)sp.a_bytes >> 4;
+    const uint32_t btile16 = (uint32_t)sp.b_tile_bytes >> 4;
+    const uint32_t a_lo_first = desc_lo0 | ((smem_base & 0x3FFFFu) >> 4);
+    const uint32_t b_lo_first = desc_lo0 | (((smem_base + (uint32_t)sp.b_off) & 0x3FFFFu) >> 4);
+    const bool resident = sp.b_resident != 0;
+    const bool tracing = a.trace != nullptr;
+    uint32_t stage = 0, phase = 0;
+    uint32_t a_lo = a_lo_first, fbar = full_bar(0), ebar = empty_bar(0);
     int tn = 0;
-    if (sp.b_resident && walk.count > 0) {
+    if (resident && walk.count > 0) {
       mbar_wait(bfull_bar, 0);  // the CTA's weights are in shared memory
       tc_fence_after();
     }
@@ -352,23 +364,45 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(tempty_bar(buf), acc_phase ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_u + buf * kAccStride;
-      for (int kb = 0; kb < a.num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+      const uint32_t tbar = tfull_bar(buf);
+      uint32_t b_lo = b_lo_first;
+      // two K blocks per trip whenever both fit before the ring wraps: the two barrier polls, the
+      // descriptor moves and the issue overlap instead of forming one dependent chain per K block
+      for (uint32_t kb = 0; kb < n_kb;) {
+        const bool pair = kb + 1 < n_kb && stage + 1 < n_stages;
+        if (tracing && lane == 0) trace_ev(a, 16, tn, 7, i * a.num_kb + (int)kb);
+        const bool ok0 = mbar_try_wait(fbar, phase);
+        const bool ok1 = pair ? mbar_try_wait(fbar + 8, phase) : true;
+        if (!ok0) mbar_wait(fbar, phase);
+        if (!ok1) mbar_wait(fbar + 8, phase);
         tc_fence_after();
-        if (a.trace != nullptr && lane == 0) trace_ev(a, 16, tn, 4, i * a.num_kb + kb);
-        const uint32_t sa = smem_base + stage * sp.stage_bytes;
-        const uint32_t sb = sp.b_resident ? smem_base + sp.b_off + kb * sp.b_tile_bytes : sa + sp.a_bytes;
-        const uint64_t da = make_smem_desc<SWZ>(sa);
-        const uint64_t db = make_smem_desc<SWZ>(sb);
+        if (tracing && lane == 0) trace_ev(a, 16, tn, 4, i * a.num_kb + (int)kb);
+        const uint64_t da0 = desc_hi | a_lo;
+        const uint64_t db0 = desc_hi | (resident ? b_lo : a_lo + a16);
+        const uint64_t da1 = desc_hi | (a_lo + stage16);
+        const uint64_t db1 = desc_hi | (resident ? b_lo + btile16 : a_lo + stage16 + a16);
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < SWZ / 32; ++k)  // UMMA_K = 32 bytes of K per instruction
-            umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
-          umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-          if (kb == a.num_kb - 1) umma_commit(tfull_bar(buf));  // accumulator complete -> epilogue
+            umma_i8(tmem_d, da0 + 2 * k, db0 + 2 * k, idesc, (kb | (uint32_t)k) != 0);
+          umma_commit(ebar);  // frees the smem slot when these MMAs retire
+          if (pair) {
+#pragma unroll
+            for (int k = 0; k < SWZ / 32; ++k) umma_i8(tmem_d, da1 + 2 * k, db1 + 2 * k, idesc, 1);
+            umma_commit(ebar + 8);
+          }
+          if (kb + (pair ? 2u : 1u) == n_kb) umma_commit(tbar);  // accumulator complete -> epilogue
         }
         __syncwarp();
-        if (++stage == sp.stages) { stage = 0; phase ^= 1; }
+        const uint32_t adv = pair ? 2u : 1u;
+        kb += adv;
+        b_lo += adv * btile16;
+        a_lo += adv * stage16; fbar += 8 * adv; ebar += 8 * adv;
+        stage += adv;
+        if (stage == n_stages) {
+          stage = 0; phase ^= 1;
+          a_lo = a_lo_first; fbar = full_bar(0); ebar = empty_bar(0);
+        }
       }
     }
   } else if (warp == 3) {
@@ -657,13 +691,12 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   a.e = e;
   a.sp = make_plan(c->g, SWZ, e.res != nullptr);
   const int grid = plan_grid(c->g, a.sp, sm_count());
-  // An issuing lane may run at most ONE mbarrier phase ahead of the consumer (parity waits alias two
-  // phases apart): lanes <= pipeline depth guarantees it (a lane's previous item is < depth behind).
-  {
-    const int a_warps = 1 + (a.sp.b_resident ? 1 : 0) + (e.res == nullptr ? 1 : 0);
-    a.prod_lanes = std::max(1, std::min(4, a.sp.stages / a_warps));  // a_warps * lanes <= stages
-  }
-  a.res_lanes = std::min(2, std::max(a.sp.res_bufs, 1));
+  // ONE issuing lane per producer warp: two lanes of a warp that sleep in mbarrier.try_wait on different
+  // barriers delay each other's wake-up by ~1.5k cycles (timeline: tools/trace_conv.py), while separate
+  // warps wake within ~100 cycles.  (An issuer may run at most one mbarrier phase ahead of the consumer
+  // -- parity waits alias two phases apart -- which holds because issuers <= pipeline depth.)
+  a.prod_lanes = 1;
+  a.res_lanes = 1;
   a.trace = g_trace;
   a.trace_cap = g_trace_cap;
   a.a_im2col = c->a_im2col;

@@ -42,7 +42,7 @@ ev[:, 0] -= 1
 n = len(ev)
 ev = ev[np.argsort(ev[:, 2], kind="stable")]
 t0 = ev[0, 2]
-names = {0: "A issue>", 1: "A issue<", 2: "B issue>", 3: "B issue<", 4: "MMA kb", 5: "EPI begin", 6: "EPI end"}
+names = {0: "A issue>", 1: "A issue<", 2: "B issue>", 3: "B issue<", 4: "MMA kb", 5: "EPI begin", 6: "EPI end", 7: "MMA wait"}
 print("events", n)
 for evn, idx, t, who in ev[:int(os.environ.get("TRACE_ROWS", "160"))]:
     print("%8d  %-10s %4d  (issuer %d)" % (t - t0, names[int(evn)], idx, who))
@@ -50,7 +50,7 @@ mma = ev[ev[:, 0] == 4]
 if len(mma) > 10:
     d = np.diff(mma[:, 2])
     print("MMA k-block period: median %.0f mean %.0f clk over %d" % (np.median(d), d.mean(), len(d)))
-for a_, b_, nm in ((0, 1, "A"), (2, 3, "B")):
+for a_, b_, nm in ((0, 1, "A"), (2, 3, "B"), (7, 4, "MMA full-wait")):
     s_ = {int(i): t for e_, i, t, _w in ev if e_ == a_}
     f_ = {int(i): t for e_, i, t, _w in ev if e_ == b_}
     dd = [f_[i] - s_[i] for i in s_ if i in f_]
