@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-agree", action="store_true", help="skip the fp32 agreement check (torch kernels)")
     ap.add_argument("--simt", action="store_true", help="run the dp4a checker kernels instead (debug)")
+    ap.add_argument("--layers", default="", help="write the per-layer CUDA-event table to this file")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -268,16 +269,33 @@ def main():
     value = world * B * args.steps / (ms * 1e-3)
 
     # ---- e2e: the public call net(x) with host buffers: H2D + forward + D2H every step ---------
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        _ = net(x_host.to(dev, non_blocking=True)).cpu()
+    # The loader-side pattern of the reference (functions.py:110-113: inputs.to(device); net(inputs))
+    # with pinned memory and a copy stream: batch i+1 crosses PCIe while batch i computes; every
+    # step's logits come back to the host (a blocking read), so nothing is deferred past the region.
+    e2e_steps = max(3, min(args.steps, 20))
+    copy_stream = torch.cuda.Stream(dev)
+    dbuf = [torch.empty_like(x), torch.empty_like(x)]
+
+    def fetch(i):  # host -> device copy of step i's input on the copy stream
+        with torch.cuda.stream(copy_stream):
+            dbuf[i % 2].copy_(x_host, non_blocking=True)
+
+    def e2e_loop(n):
+        fetch(0)
+        out = None
+        for i in range(n):
+            st.wait_stream(copy_stream)       # step i's input has landed
+            if i + 1 < n:
+                fetch(i + 1)                  # dbuf[(i+1)%2] was last read by step i-1, which has finished
+            out = net(dbuf[i % 2]).cpu()      # forward + D2H of the logits (synchronises)
+        return out
+
+    e2e_loop(2)
     barrier()
     t0 = torch.cuda.Event(enable_timing=True)
     t1 = torch.cuda.Event(enable_timing=True)
     t0.record(st)
-    for _ in range(e2e_steps):
-        xd = x_host.to(dev, non_blocking=True)
-        out_host = net(xd).cpu()
+    out_host = e2e_loop(e2e_steps)
     t1.record(st)
     barrier()
     e2e_ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
@@ -310,6 +328,13 @@ def main():
         conv_ops += ops
         conv_bytes += byts
         per_layer.append((t, ops, byts))
+    if args.layers and rank == 0:
+        with open(args.layers, "w") as f:
+            f.write("idx Cin Cout k s H M w16 res  us  TOPS  GB/s\n")
+            for i, ((t, ops, byts), op) in enumerate(zip(per_layer, eng.ops)):
+                f.write("%2d %4d %4d %d %d %3d %7d %d %d  %7.1f %7.1f %7.1f\n" % (
+                    i, op.Cin, op.Cout, op.k, op.stride, op.H, op.M, op.w16, 1 if op.res_id >= 0 else 0,
+                    1e3 * t, ops / (t * 1e-3) / 1e12, byts / (t * 1e-3) / 1e9))
     achieved_tops = conv_ops / (conv_ms * 1e-3) / 1e12
     int8_peak = 2.0 * peaks["bf16"]  # dense INT8 = 2x the measured dense bf16 tensor throughput
     roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TFLOP/s",
@@ -332,7 +357,8 @@ def main():
                    "activation_quant": "static per-tensor u8 (calibrated on one batch)"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
-                "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
+                "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps,
+                "overlap": "double-buffered pinned H2D on a copy stream; blocking D2H of the logits each step"},
         "gpu_launches": int(eng.kernel_launches * args.steps),
         "roofline": roofline,
         "pct_int8_peak_whole_net": 100.0 * (value / world) * GOP_PER_IMG[args.arch] * 1e9 / (int8_peak * 1e12),

@@ -1,21 +1,29 @@
-// csrc/stem_umma.cu -- the un-quantised stem on Blackwell tensor cores.
+// csrc/stem_umma.cu -- the un-quantised stem on Blackwell tensor cores, ONE fused kernel.
 //
 // Replaces resnet.py:206-209 (conv1 7x7 s2 p3, 3->64, fp32 weights; bn1; relu; maxpool 3x3 s2 p1).
 // The reference keeps these weights in fp32, so this layer is NOT quantised to 8 bit:
 // operands go through the tensor core as fp16 (11-bit significand, fp32 accumulation in TMEM),
 // a relative error ~3e-4, an order of magnitude below the u8 activation quantisation that follows.
 //
-// Data path (3 launches):
-//   1. stem_prep_kernel   x fp32 NCHW -> xr fp16 [N, Hr, Wc, 32]: for every input row hh and output
-//      column q the 7 taps x 4 channels (3 + zero pad) window = 32 contiguous halfs.  An implicit
-//      GEMM over a 3-channel NHWC image cannot be fed by TMA directly (6-byte pixels), this
-//      row-wise expansion (2.7x of the fp32 image) is what makes every A tile one contiguous
-//      7 KB TMA box.
-//   2. stem_umma_kernel   one tile = one output row (n, p): D[q, oc] = sum_r xr[n, 2p+r, q, :] . W[oc, r, :]
-//      7 K-blocks of 32 halfs, tcgen05.mma kind::f16 M=128 N=64 K=16, epilogue = folded BN + ReLU
-//      (+ u8 quantisation with the POOLED tensor's scale: max-pooling commutes with a monotone map).
-//   3. stem_pool_u8_kernel  3x3 s2 max-pool on the u8 NHWC tensor.
+// Data path: the fp32 NCHW image is read from HBM exactly once and the pooled u8 NHWC tensor is
+// written exactly once; im2col, the conv output and the pre-pool rows never leave the SM.
+//   work unit  = (image, 14 pooled rows) -> 29 conv rows (one recomputed at the seam), units are
+//                dealt round-robin to one persistent CTA per SM
+//   builders   (warps 0-7)  fp32 input rows -> fp16 row ring in smem (next row's loads are in flight
+//                while this row is built) -> implicit-GEMM A tile of one conv row in the UMMA
+//                K-major SWIZZLE_128B layout: row = output column q, K = (c, r, s padded to 8):
+//                every 16-byte chunk is the 8 consecutive input pixels x[c][2p-3+r][2q-3 .. 2q+4]
+//   MMA        (warps 16,17) D[128 x 64] = A[128 x 192] * W[64 x 192]^T, tcgen05.mma kind::f16, weights
+//                resident in smem, A and the TMEM accumulator double-buffered.  One thread gets a
+//                tcgen05.mma out only every ~100 cycles whatever its size (32 tensor cycles here), so
+//                even and odd conv rows are issued by two different warps
+//   epilogue   (warps 8-15) tcgen05.ld -> folded BN + ReLU -> u8 (scale of the POOLED tensor: max
+//                commutes with a monotone map) -> 4-row ring in smem -> 3x3/s2 max-pool -> coalesced
+//                stores of the pooled row
+// Calibration (SLQ_OUT_F32) writes the fp32 conv rows to a scratch tensor and pools them with the
+// fp32 pool kernel of layers.cu.
 #include <algorithm>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <new>
 
@@ -23,250 +31,322 @@
 #include "umma_ptx.cuh"
 
 struct slq_stem {
-  int N, H, W, Hc, Wc, Hp, Wp, Hr;
-  __half *xr;        // [N, Hr, Wc, 32]
-  uint8_t *conv_u8;  // [N, Hc, Wc, 64]
-  __half *wh;        // [64, 7*32]
-  CUtensorMap tmA, tmB;
+  int N, H, W, Hc, Wc, Hp, Wp;
+  __half *wh;  // [64, 192] fp16, K order (c*7 + r)*8 + s, zero padded
   int num_ctas;
 };
 
 namespace slq {
 
-constexpr int kStemStages = 8;
-constexpr int kStemABytes = 128 * 64;  // 128 pixel rows x 32 halfs
-constexpr int kStemBBytes = 64 * 64;   // 64 output channels x 32 halfs
-constexpr int kStemStageBytes = kStemABytes + kStemBBytes;
-constexpr int kStemSmemBytes = 1024 + kStemStages * kStemStageBytes + 64 * 8 + 256;
-constexpr int kStemTmemCols = 128;  // 2 accumulator buffers x 64 columns
+constexpr int kSfK = 192;                       // padded K: 24 chunks of 8 halfs (21 real)
+constexpr int kSfChunks = 24;
+constexpr int kSfABytes = 3 * 16384;            // one A tile: 3 K blocks x (128 rows x 128 B)
+constexpr int kSfBBytes = 3 * 8192;             // weights: 3 K blocks x (64 rows x 128 B)
+constexpr int kSfRowP = 264;                    // halfs per ring row: column cc = w + 3, w in [-3, 2*127+4]
+constexpr int kSfRing = 16;                     // input rows kept (7 live + 2 arriving fit twice)
+constexpr int kSfRingBytes = kSfRing * 3 * kSfRowP * 2;
+constexpr int kSfConvRing = 4;                  // u8 conv rows kept for pooling
+constexpr int kSfConvRowBytes = 128 * 64;
+constexpr int kSfAOff = 0;
+constexpr int kSfBOff = kSfAOff + 2 * kSfABytes;
+constexpr int kSfRingOff = kSfBOff + kSfBBytes;
+constexpr int kSfConvOff = kSfRingOff + ((kSfRingBytes + 1023) / 1024) * 1024;
+constexpr int kSfPrmOff = kSfConvOff + kSfConvRing * kSfConvRowBytes;
+constexpr int kSfBarOff = kSfPrmOff + 64 * 8;
+constexpr int kSfSmemBytes = 1024 + kSfBarOff + 128;
+constexpr int kSfThreads = 18 * 32;  // 8 builder + 8 epilogue + 2 MMA warps
+constexpr int kSfBuilders = 256, kSfEpi = 256;
+constexpr int kSfUnitRows = 14;                 // pooled rows per work unit
+constexpr int kSfTmemCols = 128;                // 2 accumulators x 64 columns
+static_assert(kSfSmemBytes <= 232448, "stem kernel exceeds 227 KB of shared memory");
 
-__global__ void __launch_bounds__(256) stem_prep_kernel(const float *__restrict__ x, int N, int H, int W,
-                                                        int Hr, int Wc, __half *__restrict__ xr) {
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;  // (n, hh, q)
-  const long long total = (long long)N * Hr * Wc;
-  if (idx >= total) return;
-  const int q = (int)(idx % Wc);
-  const int hh = (int)((idx / Wc) % Hr);
-  const int n = (int)(idx / ((long long)Wc * Hr));
-  const int h = hh - 3;
-  __align__(16) __half v[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __float2half_rn(0.f);
-  if (h >= 0 && h < H) {
-#pragma unroll
-    for (int s = 0; s < 7; ++s) {
-      const int w = 2 * q + s - 3;
-      if (w >= 0 && w < W) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          v[s * 4 + c] = __float2half_rn(__ldg(x + (((long long)n * 3 + c) * H + h) * W + w));
-      }
-    }
-  }
-  uint4 *dst = reinterpret_cast<uint4 *>(xr + idx * 32);
-  const uint4 *src = reinterpret_cast<const uint4 *>(v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) dst[i] = src[i];
-}
-
-// w fp32 [64, 3, 7, 7] -> wh fp16 [64, 7, 32]: wh[oc][r][s*4 + c]
+// w fp32 [64, 3, 7, 7] -> wh fp16 [64, 192]: wh[oc][(c*7 + r)*8 + s], zero for s == 7 and the pad chunks
 __global__ void stem_weights_kernel(const float *__restrict__ w, __half *__restrict__ wh) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 64 * 7 * 32) return;
-  const int j = idx & 31, r = (idx >> 5) % 7, oc = idx / (7 * 32);
-  const int s = j >> 2, c = j & 3;
+  if (idx >= 64 * kSfK) return;
+  const int k = idx % kSfK, oc = idx / kSfK;
+  const int chunk = k >> 3, s = k & 7;
   float v = 0.f;
-  if (s < 7 && c < 3) v = w[((oc * 3 + c) * 7 + r) * 7 + s];
+  if (chunk < 21 && s < 7) {
+    const int c = chunk / 7, r = chunk % 7;
+    v = w[((oc * 3 + c) * 7 + r) * 7 + s];
+  }
   wh[idx] = __float2half_rn(v);
 }
 
 struct StemArgs {
-  int N, Hc, Wc, Hr;
+  const float *x;
+  int N, H, W, Hc, Wc, Hp, Wp;
+  const __half *wh;
   const float *bn_a, *bn_b, *act_scales;
   int out_id, out_mode;
-  void *out;  // u8 [N,Hc,Wc,64] or fp32 [N,Hc,Wc,64]
+  void *out;  // u8 pooled [N,Hp,Wp,64]  |  fp32 conv rows [N,Hc,Wc,64] (SLQ_OUT_F32)
+  int units_per_img, total_units;
+  int dbg;  // $SLQ_STEM_DBG bit mask (timing experiments only): 1 skip A build, 2 skip pooling, 4 skip epilogue math
 };
 
-__global__ void __launch_bounds__(256, 1)
-stem_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const StemArgs a) {
+// A load whose ISSUE POINT the compiler must keep: __ldg() is an invariant load that gets sunk to its
+// first use (after the A-tile build), which exposes the whole DRAM latency once per conv row.
+__device__ __forceinline__ float ldg_pinned(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// conv rows [p0, p1) of unit u and the pooled rows [j0, j1) it owns
+__device__ __forceinline__ void unit_rows(const StemArgs &a, int u, int &n, int &j0, int &j1, int &p0, int &p1) {
+  n = u / a.units_per_img;
+  const int q = u - n * a.units_per_img;
+  j0 = q * kSfUnitRows;
+  j1 = min(j0 + kSfUnitRows, a.Hp);
+  p0 = max(2 * j0 - 1, 0);
+  p1 = min(2 * j1, a.Hc);  // last conv row needed is 2*(j1-1)+1
+}
+
+__global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-  float2 *prm = reinterpret_cast<float2 *>(smem + kStemStages * kStemStageBytes);  // {bn_a, bn_b} x 64
-  const uint32_t bar_base = smem_base + kStemStages * kStemStageBytes + 64 * 8;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (kStemStages + s); };
-  auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kStemStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kStemStages + 2 + b); };
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(
-      smem + kStemStages * kStemStageBytes + 64 * 8 + 8 * (2 * kStemStages + 4));
+  const uint32_t bar_base = smem_base + kSfBarOff;
+  auto afull_bar = [&](int b) { return bar_base + 8u * b; };         // A tile built      (256 arrivals)
+  auto aempty_bar = [&](int b) { return bar_base + 8u * (2 + b); };  // A tile consumed   (commit)
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (4 + b); };   // accumulator ready (commit)
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (6 + b); };  // accumulator drained (256)
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kSfBarOff + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long total_tiles = (long long)a.N * a.Hc;
 
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStemStages; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
     for (int b = 0; b < 2; ++b) {
+      mbar_init(afull_bar(b), kSfBuilders);
+      mbar_init(aempty_bar(b), 1);
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), 128);
+      mbar_init(tempty_bar(b), kSfEpi);
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void *)tmem_slot)),
-                 "r"(kStemTmemCols)
+                 "r"(kSfTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (threadIdx.x < 64) prm[threadIdx.x] = make_float2(a.bn_a[threadIdx.x], a.bn_b[threadIdx.x]);
+  // zero the input ring (its pad columns are never written again) and stage weights + BN constants
+  for (int i = threadIdx.x; i < kSfRingBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(smem + kSfRingOff)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 64 * kSfChunks; i += blockDim.x) {
+    const int oc = i / kSfChunks, j = i % kSfChunks;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.wh + oc * kSfK + j * 8));
+    const int kb = j >> 3, cj = j & 7;
+    *reinterpret_cast<uint4 *>(smem + kSfBOff + kb * 8192 + oc * 128 + ((cj ^ (oc & 7)) << 4)) = v;
+  }
+  if (threadIdx.x < 64) {  // u8 output: the re-quantisation multiply is folded into the BN constants
+    const float inv = a.out_mode == SLQ_OUT_F32 ? 1.f : __fdiv_rn(1.0f, a.act_scales[a.out_id]);
+    reinterpret_cast<float2 *>(smem + kSfPrmOff)[threadIdx.x] =
+        make_float2(__fmul_rn(a.bn_a[threadIdx.x], inv), __fmul_rn(a.bn_b[threadIdx.x], inv));
+  }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    if (lane == 0) {  // ---- TMA producer
-      int stage = 0;
-      uint32_t phase = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n = (int)(tile / a.Hc), p = (int)(tile % a.Hc);
-        for (int r = 0; r < 7; ++r) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * kStemStageBytes;
-          mbar_expect_tx(full_bar(stage), kStemStageBytes);
-          tma_load_3d(sa, &tmA, full_bar(stage), 0, 0, n * a.Hr + 2 * p + r);
-          tma_load_2d(sa + kStemABytes, &tmB, full_bar(stage), r * 32, 0);
-          if (++stage == kStemStages) { stage = 0; phase ^= 1; }
+  if (warp < 8) {
+    // ================================ builders ================================================
+    const int t = threadIdx.x;                       // 0..255
+    const int q = t & 127, jpar = t >> 7;            // output column, chunk parity
+    __half *ring = reinterpret_cast<__half *>(smem + kSfRingOff);
+    constexpr int kMaxPer = 6;                       // ring elements per thread per step (2 rows x 3 x 256 / 256)
+    int rc = 0;                                      // conv rows built so far (A buffer parity / phase)
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+      int n, j0, j1, p0, p1;
+      unit_rows(a, u, n, j0, j1, p0, p1);
+      const float *xn = a.x + (long long)n * 3 * a.H * a.W;
+      // rows [lo, hi) of the image (may be outside: zeros) -> ring, through registers
+      auto load_rows = [&](int lo, int hi, float (&v)[kMaxPer], bool first) {
+        const int per_row = 3 * a.W;
+        const int total = (hi - lo) * per_row;
+        if (first) {  // unit start: 7 rows at once, written straight away
+          for (int e = t; e < total; e += kSfBuilders) {
+            const int ri = e / per_row, rem = e - ri * per_row;
+            const int c = rem / a.W, w = rem - c * a.W;
+            const int h = lo + ri;
+            const float f = (h >= 0 && h < a.H) ? __ldg(xn + ((long long)c * a.H + h) * a.W + w) : 0.f;
+            ring[(((h + 16) & (kSfRing - 1)) * 3 + c) * kSfRowP + w + 3] = __float2half_rn(f);
+          }
+          return;
+        }
+        // steady state: two rows x three channels, one column per thread (W <= 256): no divisions
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+          const int ri = i / 3, c = i % 3;
+          const int h = lo + ri;
+          v[i] = 0.f;
+          if (t < a.W && ri < hi - lo && h >= 0 && h < a.H) v[i] = ldg_pinned(xn + ((long long)c * a.H + h) * a.W + t);
+        }
+      };
+      auto store_rows = [&](int lo, int hi, const float (&v)[kMaxPer]) {
+#pragma unroll
+        for (int i = 0; i < kMaxPer; ++i) {
+          const int ri = i / 3, c = i % 3;
+          const int h = lo + ri;
+          if (t < a.W && ri < hi - lo)
+            ring[(((h + 16) & (kSfRing - 1)) * 3 + c) * kSfRowP + t + 3] = __float2half_rn(v[i]);
+        }
+      };
+      float nxt[kMaxPer];
+      named_bar_sync(1, kSfBuilders);  // nobody still builds from the previous unit's rows
+      load_rows(2 * p0 - 3, 2 * p0 + 4, nxt, true);
+      named_bar_sync(1, kSfBuilders);
+      for (int p = p0; p < p1; ++p, ++rc) {
+        const int ab = rc & 1;
+        if (p + 1 < p1 && !(a.dbg & 16)) load_rows(2 * p + 4, 2 * p + 6, nxt, false);  // in flight during the build
+        mbar_wait(aempty_bar(ab), (uint32_t)(((rc >> 1) & 1) ^ 1));
+        uint8_t *atile = smem + kSfAOff + ab * kSfABytes;
+#pragma unroll 4
+        for (int j = jpar; j < ((a.dbg & 1) ? 0 : kSfChunks); j += 2) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (j < 21) {
+            const int c = j / 7, r = j - c * 7;
+            const int h = 2 * p - 3 + r;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(
+                ring + (((h + 16) & (kSfRing - 1)) * 3 + c) * kSfRowP + 2 * q);
+            v = make_uint4(src[0], src[1], src[2], src[3]);
+          }
+          const int kb = j >> 3, cj = j & 7;
+          *reinterpret_cast<uint4 *>(atile + kb * 16384 + q * 128 + ((cj ^ (q & 7)) << 4)) = v;
+        }
+        if (!(a.dbg & 8)) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(afull_bar(ab));
+        if (p + 1 < p1) {
+          if (!(a.dbg & 16)) store_rows(2 * p + 4, 2 * p + 6, nxt);
+          named_bar_sync(1, kSfBuilders);  // the next row's inputs are complete
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {  // ---- MMA issuer: D=f32, A=B=f16, K-major, M=128, N=64
-      const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      long long it = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        const int buf = (int)(it & 1);
-        mbar_wait(tempty_bar(buf), (uint32_t)(((it >> 1) & 1) ^ 1));
+  } else if (warp >= 16) {
+    // ================================ MMA issuers (convergent warps, elected lane) =============
+    const int my_par = warp - 16;  // this warp issues the rows with rc % 2 == my_par
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    int rc = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+      int n, j0, j1, p0, p1;
+      unit_rows(a, u, n, j0, j1, p0, p1);
+      for (int p = p0; p < p1; ++p, ++rc) {
+        const int ab = rc & 1;
+        if (ab != my_par) continue;
+        const uint32_t ph = (uint32_t)((rc >> 1) & 1);
+        mbar_wait(tempty_bar(ab), ph ^ 1);
+        mbar_wait(afull_bar(ab), ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + buf * 64;
-        for (int r = 0; r < 7; ++r) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * kStemStageBytes;
-          const uint64_t da = make_smem_desc<64>(sa);
-          const uint64_t db = make_smem_desc<64>(sa + kStemABytes);
+        const uint32_t tmem_d = tmem_u + ab * 64;
+        const uint64_t da = make_smem_desc<128>(smem_base + kSfAOff + ab * kSfABytes);
+        const uint64_t db = make_smem_desc<128>(smem_base + kSfBOff);
+        if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k)  // UMMA_K = 16 halfs = 32 bytes
-            umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (r | k) != 0);
-          umma_commit(empty_bar(stage));
-          if (++stage == kStemStages) { stage = 0; phase ^= 1; }
+          for (int kb = 0; kb < 3; ++kb)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)  // UMMA_K = 16 halfs = 32 bytes
+              umma_f16(tmem_d, da + (uint64_t)(kb * (16384 >> 4) + 2 * k), db + (uint64_t)(kb * (8192 >> 4) + 2 * k),
+                       idesc, (kb | k) != 0);
+          umma_commit(aempty_bar(ab));
+          umma_commit(tfull_bar(ab));
         }
-        umma_commit(tfull_bar(buf));
+        __syncwarp();
       }
     }
-  } else if (warp >= 4) {  // ---- epilogue: folded BN + ReLU (+ u8 quantisation)
-    const int wq = warp & 3;
-    const float inv_out = a.out_mode == SLQ_OUT_F32 ? 1.f : __fdiv_rn(1.0f, a.act_scales[a.out_id]);
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = (int)(it & 1);
-      mbar_wait(tfull_bar(buf), (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + buf * 64;
-      const int q = wq * 32 + lane;
-      const bool valid = q < a.Wc;
-      const long long pix = tile * a.Wc + q;  // tile == n*Hc + p
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+  } else {
+    // ================================ epilogue + pooling (warps 8-15) ==========================
+    const int et = threadIdx.x - kSfBuilders;        // 0..255
+    const int wq = warp & 3, half = (warp - 8) >> 2; // TMEM lane quarter, channel half
+    const int q = wq * 32 + lane;
+    const float2 *prm = reinterpret_cast<const float2 *>(smem + kSfPrmOff);
+    uint8_t *cring = smem + kSfConvOff;
+    const bool f32_out = a.out_mode == SLQ_OUT_F32;
+    int rc = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+      int n, j0, j1, p0, p1;
+      unit_rows(a, u, n, j0, j1, p0, p1);
+      for (int p = p0; p < p1; ++p, ++rc) {
+        const int ab = rc & 1;
+        mbar_wait(tfull_bar(ab), (uint32_t)((rc >> 1) & 1));
+        tc_fence_after();
         uint32_t acc[32];
-        tmem_ld32(trow + ch * 32, acc);
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + ab * 64 + half * 32, acc);
         tmem_ld_wait();
-        if (!valid) continue;
+        tc_fence_before();
+        mbar_arrive(tempty_bar(ab));  // accumulator is in registers: the next row may start
+        if (a.dbg & 4) continue;
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float2 p2 = prm[ch * 32 + j];
-          y[j] = fmaxf(__fadd_rn(__fmul_rn(__uint_as_float(acc[j]), p2.x), p2.y), 0.f);
+          const float2 p2 = prm[half * 32 + j];
+          y[j] = __fmaf_rn(__uint_as_float(acc[j]), p2.x, p2.y);  // u8: in units of the output scale
         }
-        if (a.out_mode == SLQ_OUT_F32) {
-          float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.out) + pix * 64 + ch * 32);
+        if (f32_out) {
+          if (q < a.Wc) {
+            float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.out) +
+                                                   (((long long)n * a.Hc + p) * a.Wc + q) * 64 + half * 32);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        } else {
-          uint32_t pk[8];
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f), fmaxf(y[4 * j + 2], 0.f),
+                                 fmaxf(y[4 * j + 3], 0.f));
+          }
+          continue;
+        }
+        uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            pk[j] = epi_quant_u8(__fmul_rn(y[4 * j], inv_out)) | (epi_quant_u8(__fmul_rn(y[4 * j + 1], inv_out)) << 8) |
-                    (epi_quant_u8(__fmul_rn(y[4 * j + 2], inv_out)) << 16) | (epi_quant_u8(__fmul_rn(y[4 * j + 3], inv_out)) << 24);
-          uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) + pix * 64 + ch * 32);
-          o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int j = 0; j < 8; ++j)  // saturation at 0 is the ReLU
+          pk[j] = epi_pack4<false>(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        uint4 *dst = reinterpret_cast<uint4 *>(cring + (p & (kSfConvRing - 1)) * kSfConvRowBytes + q * 64 + half * 32);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        named_bar_sync(2, kSfEpi);  // conv row p is complete in the ring
+        // pooled row j = max over conv rows 2j-1..2j+1: complete after an odd row or the last row
+        if (!((p & 1) || p == a.Hc - 1) || (a.dbg & 2)) continue;
+        const int j = p >> 1;
+        if (j < j0) continue;  // the seam row only feeds this unit's first pooled row
+        const int r_lo = max(2 * j - 1, 0), r_hi = min(2 * j + 1, a.Hc - 1);
+        uint32_t *orow = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a.out) +
+                                                      (((long long)n * a.Hp + j) * a.Wp) * 64);
+        for (int idx = et; idx < a.Wp * 16; idx += kSfEpi) {
+          const int i = idx >> 4, cw = idx & 15;
+          const int c_lo = max(2 * i - 1, 0), c_hi = min(2 * i + 1, a.Wc - 1);
+          uint32_t m = 0;  // inputs are post-ReLU: 0 is the identity of max
+          for (int r = r_lo; r <= r_hi; ++r) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(cring + (r & (kSfConvRing - 1)) * kSfConvRowBytes);
+            for (int c = c_lo; c <= c_hi; ++c) m = __vmaxu4(m, row[c * 16 + cw]);
+          }
+          orow[idx] = m;
         }
       }
-      tc_fence_before();
-      mbar_arrive(tempty_bar(buf));
     }
   }
+
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 16) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kStemTmemCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kSfTmemCols) : "memory");
   }
-}
-
-// 3x3 stride-2 pad-1 max-pool on u8 NHWC (C = 64): one thread per (pixel, 16 channels)
-__global__ void __launch_bounds__(256) stem_pool_u8_kernel(const uint8_t *__restrict__ y, int N, int Hc, int Wc,
-                                                           int Hp, int Wp, uint8_t *__restrict__ out) {
-  const long long total = (long long)N * Hp * Wp * 4;
-  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int g = (int)(idx & 3);
-  const long long pix = idx >> 2;
-  const int wp = (int)(pix % Wp), hp = (int)((pix / Wp) % Hp), n = (int)(pix / ((long long)Wp * Hp));
-  uint4 m = make_uint4(0, 0, 0, 0);
-  for (int r = 0; r < 3; ++r) {
-    const int h = 2 * hp - 1 + r;
-    if (h < 0 || h >= Hc) continue;
-    for (int s = 0; s < 3; ++s) {
-      const int w = 2 * wp - 1 + s;
-      if (w < 0 || w >= Wc) continue;
-      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(y + (((long long)n * Hc + h) * Wc + w) * 64) + g);
-      m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
-    }
-  }
-  reinterpret_cast<uint4 *>(out + pix * 64)[g] = m;
 }
 
 }  // namespace slq
 
 using namespace slq;
 
-static void stem_dims(int H, int W, int *Hc, int *Wc, int *Hp, int *Wp, int *Hr) {
+static void stem_dims(int H, int W, int *Hc, int *Wc, int *Hp, int *Wp) {
   *Hc = (H + 6 - 7) / 2 + 1;
   *Wc = (W + 6 - 7) / 2 + 1;
   *Hp = (*Hc + 2 - 3) / 2 + 1;
   *Wp = (*Wc + 2 - 3) / 2 + 1;
-  *Hr = 2 * (*Hc - 1) + 7;
 }
-
-static int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
 extern "C" int64_t slq_stem_workspace_bytes(int32_t N, int32_t H, int32_t W) {
   if (N <= 0 || H < 7 || W < 7) return -1;
-  int Hc, Wc, Hp, Wp, Hr;
-  stem_dims(H, W, &Hc, &Wc, &Hp, &Wp, &Hr);
-  return align256((int64_t)N * Hr * Wc * 32 * 2) + align256((int64_t)N * Hc * Wc * 64) + align256(64 * 7 * 32 * 2);
+  return 64 * kSfK * 2;  // the fp16 weight matrix; activations never leave the SM
 }
 
 extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace, slq_stem **out) {
@@ -276,64 +356,18 @@ extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace,
   slq_stem *s = new (std::nothrow) slq_stem();
   SLQ_CHECK_ARG(s != nullptr, "slq_stem_create: out of host memory");
   s->N = N; s->H = H; s->W = W;
-  stem_dims(H, W, &s->Hc, &s->Wc, &s->Hp, &s->Wp, &s->Hr);
-  if (s->Wc > 128) {
+  stem_dims(H, W, &s->Hc, &s->Wc, &s->Hp, &s->Wp);
+  if (s->Wc > 128 || 3 * W > 3 * 256) {
     delete s;
     set_error("slq_stem_create: the tcgen05 stem maps one output row to one 128-pixel tile (W <= 256); use slq_stem_forward");
     return SLQ_ERR_UNSUPPORTED;
   }
-  uint8_t *ws = reinterpret_cast<uint8_t *>(workspace);
-  s->xr = reinterpret_cast<__half *>(ws);
-  ws += align256((int64_t)N * s->Hr * s->Wc * 32 * 2);
-  s->conv_u8 = ws;
-  ws += align256((int64_t)N * s->Hc * s->Wc * 64);
-  s->wh = reinterpret_cast<__half *>(ws);
-  // tensor maps
-  void *p = nullptr;
-  cudaDriverEntryPointQueryResult qr;
-  cudaError_t ce = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr);
-  if (ce != cudaSuccess || qr != cudaDriverEntryPointSuccess || !p) {
-    delete s;
-    set_error("slq_stem_create: cuTensorMapEncodeTiled unavailable");
-    return SLQ_ERR_CUDA;
-  }
-  typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-  EncodeTiledFn enc = (EncodeTiledFn)p;
-  {
-    cuuint64_t dims[3] = {32, (cuuint64_t)s->Wc, (cuuint64_t)N * s->Hr};
-    cuuint64_t strides[2] = {64, (cuuint64_t)s->Wc * 64};
-    cuuint32_t box[3] = {32, 128, 1};
-    cuuint32_t es[3] = {1, 1, 1};
-    CUresult r = enc(&s->tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, s->xr, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      delete s;
-      set_error("slq_stem_create: cuTensorMapEncodeTiled(A) failed: CUresult %d", (int)r);
-      return SLQ_ERR_CUDA;
-    }
-  }
-  {
-    cuuint64_t dims[2] = {7 * 32, 64};
-    cuuint64_t strides[1] = {7 * 32 * 2};
-    cuuint32_t box[2] = {32, 64};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&s->tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, s->wh, dims, strides, box, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      delete s;
-      set_error("slq_stem_create: cuTensorMapEncodeTiled(B) failed: CUresult %d", (int)r);
-      return SLQ_ERR_CUDA;
-    }
-  }
-  s->num_ctas = (int)std::min<long long>((long long)N * s->Hc, sm_count());
+  s->wh = reinterpret_cast<__half *>(workspace);
+  const int units_per_img = (s->Hp + kSfUnitRows - 1) / kSfUnitRows;
+  s->num_ctas = (int)std::min<long long>((long long)N * units_per_img, sm_count());
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(stem_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStemSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
     if (e != cudaSuccess) {
       delete s;
       set_error("slq_stem_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -349,7 +383,7 @@ extern "C" void slq_stem_destroy(slq_stem *s) { delete s; }
 
 extern "C" int slq_stem_set_weights(slq_stem *s, const float *w, void *stream) {
   SLQ_CHECK_ARG(s && w, "slq_stem_set_weights: null pointer argument");
-  stem_weights_kernel<<<(64 * 7 * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wh);
+  stem_weights_kernel<<<(64 * kSfK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wh);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }
@@ -362,22 +396,21 @@ extern "C" int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, c
   SLQ_CHECK_ARG(out_mode == SLQ_OUT_U8 ? act_scales != nullptr : f32_scratch != nullptr,
                 "slq_stem_launch: act_scales (u8) / f32_scratch (fp32) required");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long nprep = (long long)s->N * s->Hr * s->Wc;
-  stem_prep_kernel<<<(unsigned)ceil_div(nprep, 256), 256, 0, st>>>(x, s->N, s->H, s->W, s->Hr, s->Wc, s->xr);
-  SLQ_LAUNCH_CHECK();
   StemArgs a;
-  a.N = s->N; a.Hc = s->Hc; a.Wc = s->Wc; a.Hr = s->Hr;
+  a.x = x;
+  a.N = s->N; a.H = s->H; a.W = s->W; a.Hc = s->Hc; a.Wc = s->Wc; a.Hp = s->Hp; a.Wp = s->Wp;
+  a.wh = s->wh;
   a.bn_a = bn_a; a.bn_b = bn_b; a.act_scales = act_scales; a.out_id = out_id; a.out_mode = out_mode;
-  a.out = out_mode == SLQ_OUT_U8 ? (void *)s->conv_u8 : (void *)f32_scratch;
-  stem_umma_kernel<<<s->num_ctas, 256, kStemSmemBytes, st>>>(s->tmA, s->tmB, a);
-  SLQ_LAUNCH_CHECK();
-  if (out_mode == SLQ_OUT_U8) {
-    const long long total = (long long)s->N * s->Hp * s->Wp * 4;
-    stem_pool_u8_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(s->conv_u8, s->N, s->Hc, s->Wc, s->Hp, s->Wp,
-                                                                       reinterpret_cast<uint8_t *>(out));
-  } else {
-    return launch_stem_pool(f32_scratch, s->N, s->Hc, s->Wc, s->Hp, s->Wp, act_scales, out_id, out, SLQ_OUT_F32, st);
+  a.out = out_mode == SLQ_OUT_U8 ? out : (void *)f32_scratch;
+  a.units_per_img = (s->Hp + kSfUnitRows - 1) / kSfUnitRows;
+  a.total_units = s->N * a.units_per_img;
+  {
+    const char *d = getenv("SLQ_STEM_DBG");
+    a.dbg = d ? atoi(d) : 0;
   }
+  stem_fused_kernel<<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   SLQ_LAUNCH_CHECK();
+  if (out_mode == SLQ_OUT_F32)
+    return launch_stem_pool(f32_scratch, s->N, s->Hc, s->Wc, s->Hp, s->Wp, act_scales, out_id, out, SLQ_OUT_F32, st);
   return SLQ_OK;
 }

@@ -292,7 +292,7 @@ class Engine:
         L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
                                      sc, self.final_id, self.fc_w.data_ptr(), self.fc_b.data_ptr(),
                                      self.logits.shape[1], self.pooled.data_ptr(), self.logits.data_ptr(), st))
-        self.kernel_launches = (3 if self.stem is not None else 2) + len(self.ops) + 2
+        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 2
 
     def _stem(self, x_ptr, out_ptr, mode, st):
         lib, sc = self.lib, self.act_scales.data_ptr()
