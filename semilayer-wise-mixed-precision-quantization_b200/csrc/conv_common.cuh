@@ -43,6 +43,9 @@ __host__ __device__ inline int gemm_row_of(int oc, int limb, int w16) {
 
 int validate_desc(const slq_conv_desc *d);  // SLQ_OK or error (message set)
 
+// debug timeline buffer installed by slq_debug_set_trace (conv_umma.cu); NULL when tracing is off
+void debug_trace_buffer(long long **buf, int *cap);
+
 // SIMT (dp4a) launcher, layers.cu
 int launch_conv_simt(const ConvGeom &g, const uint8_t *in, const uint8_t *wg, const EpiDev &e,
                      cudaStream_t st);

@@ -677,6 +677,7 @@ static int build_tensor_maps(slq_conv *c) {
 
 static long long *g_trace = nullptr;  // slq_debug_set_trace
 static int g_trace_cap = 0;
+void debug_trace_buffer(long long **buf, int *cap) { *buf = g_trace; *cap = g_trace_cap; }
 
 template <int SWZ, bool W16, int OUT, int RES>
 static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {

@@ -9,15 +9,15 @@
 // written exactly once; im2col, the conv output and the pre-pool rows never leave the SM.
 //   work unit  = (image, 14 pooled rows) -> 29 conv rows (one recomputed at the seam), units are
 //                dealt round-robin to one persistent CTA per SM
-//   builders   (warps 0-7)  fp32 input rows -> fp16 row ring in smem (next row's loads are in flight
+//   builders   (warps 0-15) fp32 input rows -> fp16 row ring in smem (next row's loads are in flight
 //                while this row is built) -> implicit-GEMM A tile of one conv row in the UMMA
 //                K-major SWIZZLE_128B layout: row = output column q, K = (c, r, s padded to 8):
 //                every 16-byte chunk is the 8 consecutive input pixels x[c][2p-3+r][2q-3 .. 2q+4]
-//   MMA        (warps 16,17) D[128 x 64] = A[128 x 192] * W[64 x 192]^T, tcgen05.mma kind::f16, weights
+//   MMA        (warps 24,25) D[128 x 64] = A[128 x 192] * W[64 x 192]^T, tcgen05.mma kind::f16, weights
 //                resident in smem, A and the TMEM accumulator double-buffered.  One thread gets a
 //                tcgen05.mma out only every ~100 cycles whatever its size (32 tensor cycles here), so
 //                even and odd conv rows are issued by two different warps
-//   epilogue   (warps 8-15) tcgen05.ld -> folded BN + ReLU -> u8 (scale of the POOLED tensor: max
+//   epilogue   (warps 16-23) tcgen05.ld -> folded BN + ReLU -> u8 (scale of the POOLED tensor: max
 //                commutes with a monotone map) -> 4-row ring in smem -> 3x3/s2 max-pool -> coalesced
 //                stores of the pooled row
 // Calibration (SLQ_OUT_F32) writes the fp32 conv rows to a scratch tensor and pools them with the
@@ -54,8 +54,9 @@ constexpr int kSfConvOff = kSfRingOff + ((kSfRingBytes + 1023) / 1024) * 1024;
 constexpr int kSfPrmOff = kSfConvOff + kSfConvRing * kSfConvRowBytes;
 constexpr int kSfBarOff = kSfPrmOff + 64 * 8;
 constexpr int kSfSmemBytes = 1024 + kSfBarOff + 128;
-constexpr int kSfThreads = 18 * 32;  // 8 builder + 8 epilogue + 2 MMA warps
-constexpr int kSfBuilders = 256, kSfEpi = 256;
+constexpr int kSfThreads = 26 * 32;  // 16 builder + 8 epilogue + 2 MMA warps
+constexpr int kSfBuilders = 512, kSfEpi = 256;
+constexpr int kSfBW = kSfBuilders / 32;          // builder warps; epilogue = warps kSfBW..kSfBW+7, MMA = the last two
 constexpr int kSfUnitRows = 14;                 // pooled rows per work unit
 constexpr int kSfTmemCols = 128;                // 2 accumulators x 64 columns
 static_assert(kSfSmemBytes <= 232448, "stem kernel exceeds 227 KB of shared memory");
@@ -82,8 +83,22 @@ struct StemArgs {
   int out_id, out_mode;
   void *out;  // u8 pooled [N,Hp,Wp,64]  |  fp32 conv rows [N,Hc,Wc,64] (SLQ_OUT_F32)
   int units_per_img, total_units;
+  long long *trace;  // debug timeline of CTA 0 (slq_debug_set_trace): 24 issuers x cap/24 events
+  int trace_cap;
   int dbg;  // $SLQ_STEM_DBG bit mask (timing experiments only): 1 skip A build, 2 skip pooling, 4 skip epilogue math
 };
+
+__device__ __forceinline__ void stem_trace(const StemArgs &a, int issuer, int &n, int ev, int idx) {
+  if (a.trace == nullptr || blockIdx.x != 0) return;
+  const int per = a.trace_cap / 24;
+  if (n < per) {
+    long long *p = a.trace + 3LL * (issuer * per + n);
+    p[0] = ev + 1;
+    p[1] = idx;
+    p[2] = clock64();
+    ++n;
+  }
+}
 
 // A load whose ISSUE POINT the compiler must keep: __ldg() is an invariant load that gets sunk to its
 // first use (after the A-tile build), which exposes the whole DRAM latency once per conv row.
@@ -101,6 +116,24 @@ __device__ __forceinline__ void unit_rows(const StemArgs &a, int u, int &n, int 
   j1 = min(j0 + kSfUnitRows, a.Hp);
   p0 = max(2 * j0 - 1, 0);
   p1 = min(2 * j1, a.Hc);  // last conv row needed is 2*(j1-1)+1
+}
+
+// Chunks [J0, J1) of output column q of one conv row: every index that depends on the chunk is a
+// compile-time constant after unrolling (c, r, K block, chunk-in-block), so a chunk costs 4 LDS.32 +
+// 1 STS.128 + a handful of integer ops.  ring_q = ring + 2q halfs; atile_q = tile + q*128; qx = q & 7.
+template <int J0, int J1>
+__device__ __forceinline__ void stem_build_chunks(const __half *ring_q, uint8_t *atile_q, int qx, int p) {
+#pragma unroll
+  for (int j = J0; j < J1; ++j) {
+    constexpr int dummy = 0;
+    (void)dummy;
+    const int c = j / 7, r = j % 7;
+    const int slot = (2 * p + 13 + r) & (kSfRing - 1);  // (2p - 3 + r + 16) mod 16
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(ring_q + (slot * 3 + c) * kSfRowP);
+    const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+    const int kb = j >> 3, cj = j & 7;
+    *reinterpret_cast<uint4 *>(atile_q + kb * 16384 + ((cj ^ qx) << 4)) = v;
+  }
 }
 
 __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArgs a) {
@@ -125,7 +158,7 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
     }
     fence_barrier_init();
   }
-  if (warp == 16) {
+  if (warp == kSfBW + 8) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void *)tmem_slot)),
                  "r"(kSfTmemCols)
@@ -141,6 +174,11 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
     const int kb = j >> 3, cj = j & 7;
     *reinterpret_cast<uint4 *>(smem + kSfBOff + kb * 8192 + oc * 128 + ((cj ^ (oc & 7)) << 4)) = v;
   }
+  for (int i = threadIdx.x; i < 2 * 128 * 3; i += blockDim.x) {  // K-pad chunks 21..23 of both A tiles stay zero
+    const int ab = i / 384, rem = i % 384, q = rem / 3, j = 21 + rem % 3;
+    *reinterpret_cast<uint4 *>(smem + kSfAOff + ab * kSfABytes + (j >> 3) * 16384 + q * 128 + (((j & 7) ^ (q & 7)) << 4)) =
+        make_uint4(0, 0, 0, 0);
+  }
   if (threadIdx.x < 64) {  // u8 output: the re-quantisation multiply is folded into the BN constants
     const float inv = a.out_mode == SLQ_OUT_F32 ? 1.f : __fdiv_rn(1.0f, a.act_scales[a.out_id]);
     reinterpret_cast<float2 *>(smem + kSfPrmOff)[threadIdx.x] =
@@ -152,12 +190,14 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (warp < kSfBW) {
     // ================================ builders ================================================
-    const int t = threadIdx.x;                       // 0..255
-    const int q = t & 127, jpar = t >> 7;            // output column, chunk parity
+    const int t = threadIdx.x;                       // 0..511
+    const int q = t & 127, part = t >> 7;            // output column, which quarter of the 21 chunks
+    const int lt = t & 255, lrow = t >> 8;           // loader role: input column, which of the two new rows
     __half *ring = reinterpret_cast<__half *>(smem + kSfRingOff);
-    constexpr int kMaxPer = 6;                       // ring elements per thread per step (2 rows x 3 x 256 / 256)
+    constexpr int kMaxPer = 3;                       // ring elements per thread per step: 3 channels of one row
+    int tn = 0;
     int rc = 0;                                      // conv rows built so far (A buffer parity / phase)
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
@@ -177,22 +217,19 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
           }
           return;
         }
-        // steady state: two rows x three channels, one column per thread (W <= 256): no divisions
+        // steady state: thread = (one of the two new rows, one column), three channels: no divisions
+        const int h = lo + lrow;
+        const bool ok = lt < a.W && lrow < hi - lo && h >= 0 && h < a.H;
+        const float *src = xn + (long long)h * a.W + lt;
 #pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-          const int ri = i / 3, c = i % 3;
-          const int h = lo + ri;
-          v[i] = 0.f;
-          if (t < a.W && ri < hi - lo && h >= 0 && h < a.H) v[i] = ldg_pinned(xn + ((long long)c * a.H + h) * a.W + t);
-        }
+        for (int c = 0; c < 3; ++c) v[c] = ok ? ldg_pinned(src + (long long)c * a.H * a.W) : 0.f;
       };
       auto store_rows = [&](int lo, int hi, const float (&v)[kMaxPer]) {
+        const int h = lo + lrow;
+        if (lt < a.W && lrow < hi - lo) {
+          __half *dst = ring + ((h + 16) & (kSfRing - 1)) * 3 * kSfRowP + lt + 3;
 #pragma unroll
-        for (int i = 0; i < kMaxPer; ++i) {
-          const int ri = i / 3, c = i % 3;
-          const int h = lo + ri;
-          if (t < a.W && ri < hi - lo)
-            ring[(((h + 16) & (kSfRing - 1)) * 3 + c) * kSfRowP + t + 3] = __float2half_rn(v[i]);
+          for (int c = 0; c < 3; ++c) dst[c * kSfRowP] = __float2half_rn(v[c]);
         }
       };
       float nxt[kMaxPer];
@@ -201,33 +238,32 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
       named_bar_sync(1, kSfBuilders);
       for (int p = p0; p < p1; ++p, ++rc) {
         const int ab = rc & 1;
+        if (t == 0) stem_trace(a, 0, tn, 0, rc);
         if (p + 1 < p1 && !(a.dbg & 16)) load_rows(2 * p + 4, 2 * p + 6, nxt, false);  // in flight during the build
         mbar_wait(aempty_bar(ab), (uint32_t)(((rc >> 1) & 1) ^ 1));
+        if (t == 0) stem_trace(a, 0, tn, 1, rc);
         uint8_t *atile = smem + kSfAOff + ab * kSfABytes;
-#pragma unroll 4
-        for (int j = jpar; j < ((a.dbg & 1) ? 0 : kSfChunks); j += 2) {
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (j < 21) {
-            const int c = j / 7, r = j - c * 7;
-            const int h = 2 * p - 3 + r;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(
-                ring + (((h + 16) & (kSfRing - 1)) * 3 + c) * kSfRowP + 2 * q);
-            v = make_uint4(src[0], src[1], src[2], src[3]);
-          }
-          const int kb = j >> 3, cj = j & 7;
-          *reinterpret_cast<uint4 *>(atile + kb * 16384 + q * 128 + ((cj ^ (q & 7)) << 4)) = v;
+        if (!(a.dbg & 1)) {
+          if (part == 0) stem_build_chunks<0, 6>(ring + 2 * q, atile + q * 128, q & 7, p);
+          else if (part == 1) stem_build_chunks<6, 11>(ring + 2 * q, atile + q * 128, q & 7, p);
+          else if (part == 2) stem_build_chunks<11, 16>(ring + 2 * q, atile + q * 128, q & 7, p);
+          else stem_build_chunks<16, 21>(ring + 2 * q, atile + q * 128, q & 7, p);
         }
+        if (t == 0) stem_trace(a, 0, tn, 2, rc);
         if (!(a.dbg & 8)) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(afull_bar(ab));
+        if (t == 0) stem_trace(a, 0, tn, 3, rc);
         if (p + 1 < p1) {
           if (!(a.dbg & 16)) store_rows(2 * p + 4, 2 * p + 6, nxt);
           named_bar_sync(1, kSfBuilders);  // the next row's inputs are complete
         }
+        if (t == 0) stem_trace(a, 0, tn, 8, rc);
       }
     }
-  } else if (warp >= 16) {
+  } else if (warp >= kSfBW + 8) {
     // ================================ MMA issuers (convergent warps, elected lane) =============
-    const int my_par = warp - 16;  // this warp issues the rows with rc % 2 == my_par
+    const int my_par = warp - (kSfBW + 8);  // this warp issues the rows with rc % 2 == my_par
+    int tn = 0;
     const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     int rc = 0;
@@ -241,6 +277,7 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
         mbar_wait(tempty_bar(ab), ph ^ 1);
         mbar_wait(afull_bar(ab), ph);
         tc_fence_after();
+        if (lane == 0) stem_trace(a, 16 + my_par, tn, 4, rc);
         const uint32_t tmem_d = tmem_u + ab * 64;
         const uint64_t da = make_smem_desc<128>(smem_base + kSfAOff + ab * kSfABytes);
         const uint64_t db = make_smem_desc<128>(smem_base + kSfBOff);
@@ -255,16 +292,18 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
           umma_commit(tfull_bar(ab));
         }
         __syncwarp();
+        if (lane == 0) stem_trace(a, 16 + my_par, tn, 9, rc);
       }
     }
   } else {
     // ================================ epilogue + pooling (warps 8-15) ==========================
     const int et = threadIdx.x - kSfBuilders;        // 0..255
-    const int wq = warp & 3, half = (warp - 8) >> 2; // TMEM lane quarter, channel half
+    const int wq = warp & 3, half = (warp - kSfBW) >> 2; // TMEM lane quarter, channel half
     const int q = wq * 32 + lane;
     const float2 *prm = reinterpret_cast<const float2 *>(smem + kSfPrmOff);
     uint8_t *cring = smem + kSfConvOff;
     const bool f32_out = a.out_mode == SLQ_OUT_F32;
+    int tn = 0;
     int rc = 0;
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
@@ -273,6 +312,7 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
         const int ab = rc & 1;
         mbar_wait(tfull_bar(ab), (uint32_t)((rc >> 1) & 1));
         tc_fence_after();
+        if (et == 0) stem_trace(a, 18, tn, 5, rc);
         uint32_t acc[32];
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + ab * 64 + half * 32, acc);
         tmem_ld_wait();
@@ -303,31 +343,42 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
         uint4 *dst = reinterpret_cast<uint4 *>(cring + (p & (kSfConvRing - 1)) * kSfConvRowBytes + q * 64 + half * 32);
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (et == 0) stem_trace(a, 18, tn, 10, rc);
         named_bar_sync(2, kSfEpi);  // conv row p is complete in the ring
+        if (et == 0) stem_trace(a, 18, tn, 11, rc);
         // pooled row j = max over conv rows 2j-1..2j+1: complete after an odd row or the last row
         if (!((p & 1) || p == a.Hc - 1) || (a.dbg & 2)) continue;
         const int j = p >> 1;
         if (j < j0) continue;  // the seam row only feeds this unit's first pooled row
-        const int r_lo = max(2 * j - 1, 0), r_hi = min(2 * j + 1, a.Hc - 1);
-        uint32_t *orow = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(a.out) +
-                                                      (((long long)n * a.Hp + j) * a.Wp) * 64);
-        for (int idx = et; idx < a.Wp * 16; idx += kSfEpi) {
-          const int i = idx >> 4, cw = idx & 15;
-          const int c_lo = max(2 * i - 1, 0), c_hi = min(2 * i + 1, a.Wc - 1);
-          uint32_t m = 0;  // inputs are post-ReLU: 0 is the identity of max
-          for (int r = r_lo; r <= r_hi; ++r) {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(cring + (r & (kSfConvRing - 1)) * kSfConvRowBytes);
-            for (int c = c_lo; c <= c_hi; ++c) m = __vmaxu4(m, row[c * 16 + cw]);
-          }
+        // one thread per (pooled column, 16 channels): 9 clamped 16-byte loads (a duplicated row or
+        // column does not change a max), byte-wise max, one 16-byte coalesced store
+        const int r0 = max(2 * j - 1, 0), r1 = 2 * j, r2 = min(2 * j + 1, a.Hc - 1);
+        const uint8_t *row0 = cring + (r0 & (kSfConvRing - 1)) * kSfConvRowBytes;
+        const uint8_t *row1 = cring + (r1 & (kSfConvRing - 1)) * kSfConvRowBytes;
+        const uint8_t *row2 = cring + (r2 & (kSfConvRing - 1)) * kSfConvRowBytes;
+        uint4 *orow = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) +
+                                                (((long long)n * a.Hp + j) * a.Wp) * 64);
+        for (int idx = et; idx < a.Wp * 4; idx += kSfEpi) {
+          const int i = idx >> 2, g = (idx & 3) * 16;
+          const int c0 = max(2 * i - 1, 0) * 64 + g, c1 = 2 * i * 64 + g, c2 = min(2 * i + 1, a.Wc - 1) * 64 + g;
+          uint4 m = *reinterpret_cast<const uint4 *>(row0 + c0);
+          auto mx = [&](const uint8_t *ptr) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(ptr);
+            m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
+          };
+          mx(row0 + c1); mx(row0 + c2);
+          mx(row1 + c0); mx(row1 + c1); mx(row1 + c2);
+          mx(row2 + c0); mx(row2 + c1); mx(row2 + c2);
           orow[idx] = m;
         }
+        if (et == 0) stem_trace(a, 18, tn, 6, rc);
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) {
+  if (warp == kSfBW + 8) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kSfTmemCols) : "memory");
   }
@@ -405,6 +456,9 @@ extern "C" int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, c
   a.units_per_img = (s->Hp + kSfUnitRows - 1) / kSfUnitRows;
   a.total_units = s->N * a.units_per_img;
   {
+    int cap = 0;
+    debug_trace_buffer(&a.trace, &cap);
+    a.trace_cap = cap;
     const char *d = getenv("SLQ_STEM_DBG");
     a.dbg = d ? atoi(d) : 0;
   }
