@@ -337,12 +337,24 @@ def main():
                     1e3 * t, ops / (t * 1e-3) / 1e12, byts / (t * 1e-3) / 1e9))
     achieved_tops = conv_ops / (conv_ms * 1e-3) / 1e12
     int8_peak = 2.0 * peaks["bf16"]  # dense INT8 = 2x the measured dense bf16 tensor throughput
+    # DRAM traffic of the same launches from the committed `ncu --set full` capture of one step
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "r1_ncu_full_step_summary.csv")
+    if args.arch == "resnet50" and B == 256 and os.path.exists(prof):
+        import csv
+        rows = [r for r in csv.DictReader(open(prof)) if "conv_umma" in r["kernel"]]
+        if len(rows) == len(eng.ops):
+            traffic = 1e6 * sum(float(r["dram_rd_MB"]) + float(r["dram_wr_MB"]) for r in rows) / len(rows)
     roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TFLOP/s",
-                "frac": achieved_tops / int8_peak, "traffic": None,
-                "kernel": "conv_umma_kernel (all %d conv launches of a step; ops = 2*MAC, integer)" % len(eng.ops),
-                "peak_source": "2 x %s bf16 dense (MEASURED_PEAKS.json sustained)" % peaks["src"],
+                "frac": achieved_tops / int8_peak, "traffic": traffic,
+                "traffic_note": "mean DRAM bytes (read+write) per conv launch, profiles/r1_ncu_full_step_summary.csv; "
+                                "algorithmic mean %.1f MB" % (conv_bytes / len(eng.ops) / 1e6),
+                "kernel": "conv_umma_kernel: the %d conv launches of a step, each timed with CUDA events on the "
+                          "launching stream; achieved = sum(2*MAC) / sum(duration)" % len(eng.ops),
+                "peak_source": "2 x %s bf16 dense (MEASURED_PEAKS.json sustained): INT8 tensor peak" % peaks["src"],
                 "hbm_achieved_gbs": conv_bytes / (conv_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm"],
-                "conv_ms_per_step": conv_ms, "step_share": conv_ms / (ms / args.steps)}
+                "hbm_frac": conv_bytes / (conv_ms * 1e-3) / 1e9 / peaks["hbm"],
+                "conv_ms_per_step_serialised": conv_ms, "step_ms": ms / args.steps}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -219,15 +219,6 @@ def _dist():
     return None, 0, 1
 
 
-def _base_loss(originaloutputs, loader):
-    tot, cnt = 0.0, 0
-    for p, (_x, y) in zip(originaloutputs, loader):
-        y = y.to(p.device)
-        tot += float((-torch.log(p.gather(1, y[:, None]).squeeze(1))).mean())
-        cnt += 1
-    return tot / max(cnt, 1)
-
-
 def make_semilayers(arch, net, device, originaloutputs, listminus, listplus, metric=None, shard=True):
     """Sensitivity sweep (reference functions.py:186-588, three copies): one candidate per semilayer
     = quantise its channels on fresh weights, evaluate the whole loader, sensitivity =
@@ -254,7 +245,10 @@ def make_semilayers(arch, net, device, originaloutputs, listminus, listplus, met
                 semilayers.append(cur)
                 cur = []
     factory = getattr(resnet, arch)
-    base = _base_loss(originaloutputs, imagenet.val_loader) if metric == "dloss" else None
+    # delta-loss needs the un-quantised loss from logits (the stored softmax underflows to exact zeros on
+    # random-init R34/R50, which is what makes KL NaN there): one more evaluation of the caller's net,
+    # before candidate 0 mutates it
+    base = evaluate_acc_loss_softmax(net, device, imagenet.val_loader)[1] if metric == "dloss" else None
     values = torch.zeros(len(semilayers), dtype=torch.float64)
     for index, rows in enumerate(semilayers):
         mine = (index % world) == rank

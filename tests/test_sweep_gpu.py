@@ -1,0 +1,44 @@
+"""Sharded sensitivity sweep on the GPU path (BASELINE config 4): two ranks (gloo,
+both on cuda:0 -- the box of the test run has one GPU) return the same per-candidate values as one
+process.  The NCCL variant of the same script is tools/sweep_run.py under torchrun."""
+import json
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from helpers import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(world):
+    script = os.path.join(ROOT, "tools", "sweep_run.py")
+    common = ["--arch", "resnet18", "--batches", "1", "--batch", "4", "--layers", "3", "--backend", "gloo"]
+    if world == 1:
+        cmd = [sys.executable, script] + common
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), script] + common
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    return json.loads(line)
+
+
+def test_sweep_two_ranks_equal_one_rank():
+    one, two = _run(1), _run(2)
+    assert one["world"] == 1 and two["world"] == 2
+    assert one["values_sha256"] == two["values_sha256"]  # identical floats after the all_gather
+    assert one["ranked_first8"] == two["ranked_first8"]
+    assert one["flat_rows"] == two["flat_rows"]
