@@ -11,11 +11,10 @@
 //   S[m] = sum_k A[m, k] that the zero-point correction z[oc]*S[m] needs.
 //
 // Persistent, warp-specialised CTA (640 threads, 1 CTA/SM):
-//   warp 0      TMA producer (A, B)    one lane; smem ring of kStages x {A 128xSWZ, B (bn+16)xSWZ}
-//   warp 1      tcgen05.mma issuer     one lane; accumulators double-buffered in TMEM (2 x 256 cols)
-//   warp 2      TMEM allocator
-//   warp 3      residual producer      one lane; TMA-loads the identity tile of the block
-//   warps 4-11  epilogue team 0  \  tile i -> team i&1 (= accumulator buffer i&1).  A team is 8 warps:
+//   warp 0      TMA producer (A, resident B, residual tiles); smem ring of kStages x {A 128xSWZ [, B (bn+16)xSWZ]}
+//   warp 1, 3   tcgen05.mma issuers: K blocks alternate between the two; accumulator ring of 3 in TMEM
+//   warp 2      TMEM allocator, then second A producer (resident weights) or B producer (streamed weights)
+//   warps 4-11  epilogue team 0  \  tile i -> team i&1, accumulator buffer i%3.  A team is 8 warps:
 //   warps 12-19 epilogue team 1  /  two per TMEM lane quarter, each taking half of the tile's channels:
 //               tcgen05.ld -> dequant + folded BN + residual + ReLU -> u8 into a swizzled smem tile
 //               -> ONE TMA store per tile, so the epilogue's global traffic is coalesced 128-byte
@@ -23,6 +22,7 @@
 //               (16 warps = 4 per scheduler keep it near one instruction per cycle per scheduler) and is
 //               compiled per (output kind, residual kind) so that no mode branch survives in the loop.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 
 #include "conv_common.cuh"
@@ -30,7 +30,8 @@
 
 namespace slq {
 
-constexpr int kThreads = 640;
+constexpr int kThreads = 640;   // 20 warps: 96 registers per thread (the epilogue needs them)
+constexpr int kMmaWarp1 = 3;    // second MMA-issuing warp (the first is warp 1)
 constexpr int kTeam = 256;  // threads of one epilogue team
 constexpr int kOutTileBytes = kTileM * 128;  // u8 output / residual staging tile (128 rows x <=128 B)
 
@@ -40,15 +41,18 @@ constexpr int kSmemLimit = 232448;  // 227 KB: the most dynamic shared memory on
 // Shared-memory carve-up of one layer (byte offsets from the 1024-aligned base), decided on the host.
 //   streamed B : every pipeline stage holds {A tile, B tile}; B is re-fetched for every tile.
 //   resident B : the n-tile's whole weight matrix (num_kb B tiles) stays in smem for all the M tiles a
-//                CTA works on, stages hold A only.  The TMA engine moves ~one (<=128-byte) smem row
-//                per ~4 cycles per SM, so not re-sending bn+16 weight rows per K block cuts the rows
-//                per tile by 1.3-1.9x on the small-K layers.
+//                CTA works on, stages hold A only -- `group` consecutive K blocks (A tiles) per stage, so
+//                that one barrier round trip, one expect_tx and one loop trip of the issuing warps cover
+//                several TMA boxes / MMAs (a warp's control code runs at ~5-10 cycles per dependent
+//                instruction, which is what bounds the small-K layers; tools/issue_bench.cu).
 struct SmemPlan {
-  int stages;        // A (or A+B) pipeline depth
+  int stages;        // pipeline depth (even, see make_plan)
   int stage_bytes;   // stride between stages
+  int group;         // K blocks per stage (1 when B is streamed)
   int a_bytes;       // kTileM * SWZ
   int b_tile_bytes;  // (bn_cols + 16) * SWZ
   int b_resident;    // 1: B tiles at b_off + kb * b_tile_bytes ; 0: inside each stage after A
+  int mma_warps;     // 2: warps 1 and 3 issue MMAs (1: warp 1 only; experiments)
   int b_off;
   int res_bufs;      // depth of the residual (block identity) prefetch ring, 0 without residual
   int out_off, res_off, prm_off, bar_off;
@@ -56,26 +60,43 @@ struct SmemPlan {
 };
 
 constexpr int kMaxResBufs = 4;
+constexpr int kMaxGroup = 4;
 
 inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
   SmemPlan p{};
   p.a_bytes = kTileM * swz;
   p.b_tile_bytes = (g.bn_cols + 16) * swz;
-  p.res_bufs = has_res ? kMaxResBufs : 0;
   const int num_kb = g.Ktot / swz;
-  // out staging (2), residual ring, prm, barriers, alignment slack
-  const int fixed = (2 + p.res_bufs) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
-  const int avail = kSmemLimit - fixed;
   const long long b_all = (long long)num_kb * p.b_tile_bytes;
-  if (b_all + 3LL * p.a_bytes <= avail) {
-    p.b_resident = 1;
-    p.stage_bytes = p.a_bytes;
-    p.stages = (int)std::min<long long>(kMaxStages, (avail - b_all) / p.a_bytes);
-  } else {
-    p.b_resident = 0;
-    p.stage_bytes = p.a_bytes + p.b_tile_bytes;
-    p.stages = std::min(kMaxStages, avail / p.stage_bytes);
+  static const int force_group = getenv("SLQ_GROUP") ? atoi(getenv("SLQ_GROUP")) : 0;     // experiments only
+  static const int force_mma = getenv("SLQ_MMA_WARPS") ? atoi(getenv("SLQ_MMA_WARPS")) : 0;
+  // EVEN depth: stage-sized step c goes to producer / MMA warp c & 1 and to stage c % stages, so with an
+  // even depth every stage barrier is always waited on by the same warp (an mbarrier wait only names a
+  // phase parity; a warp that saw every other phase of a barrier could not tell them apart)
+  p.stages = 0;
+  for (int rb = has_res ? kMaxResBufs : 0; p.stages == 0 && rb >= (has_res ? 2 : 0); rb -= 2) {
+    // out staging (2), residual ring, prm, barriers, alignment slack
+    const int fixed = (2 + rb) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
+    const long long room = (long long)kSmemLimit - fixed - b_all;  // for A stages when B is resident
+    for (int grp = std::min(kMaxGroup, num_kb); grp >= 1; --grp) {
+      if (num_kb % grp != 0 || (force_group && grp > force_group)) continue;
+      const int st = (int)std::min<long long>(kMaxStages, room / ((long long)grp * p.a_bytes)) & ~1;
+      if (st >= (grp == 1 ? 4 : 4)) {
+        p.b_resident = 1; p.group = grp; p.stages = st; p.stage_bytes = grp * p.a_bytes; p.res_bufs = rb;
+        break;
+      }
+    }
+    if (!has_res) break;
   }
+  if (p.stages == 0) {
+    p.res_bufs = has_res ? kMaxResBufs : 0;
+    const int fixed = (2 + p.res_bufs) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
+    p.b_resident = 0;
+    p.group = 1;
+    p.stage_bytes = p.a_bytes + p.b_tile_bytes;
+    p.stages = std::min(kMaxStages, (kSmemLimit - fixed) / p.stage_bytes) & ~1;
+  }
+  p.mma_warps = force_mma ? force_mma : 2;
   p.b_off = p.stages * p.stage_bytes;
   p.out_off = p.b_off + (p.b_resident ? (int)b_all : 0);
   p.res_off = p.out_off + 2 * kOutTileBytes;
@@ -102,10 +123,10 @@ struct KernelArgs {
   SmemPlan sp;
   int a_im2col;
   int num_kb;          // K blocks per tile = kh*kw*Cin / SWZ
+  int num_grp;         // pipeline steps per tile = num_kb / sp.group
   int chunks_per_tap;  // Cin / SWZ
   int tma_out;         // 1: u8/s8 output through the smem tile + TMA store
-  int prod_lanes;      // lanes of warp 0 that issue TMA loads (one thread sustains only ~1 box / 700 clk)
-  int res_lanes;       // lanes of warp 3 that issue residual loads
+  int mma_warps_per_tile;  // MMA warps that touch one tile: 2, or 1 when a tile is a single K block
   long long m_tiles;
   long long *trace;    // debug: CTA 0 logs (event, index, clock) triples here (slq_debug_set_trace)
   int trace_cap;
@@ -160,7 +181,9 @@ struct TileWalk {  // everything fits 32 bits (M <= 2^31): no 64-bit divisions o
   }
 };
 
-constexpr int kAccStride = 256;  // TMEM columns between the two accumulator buffers
+constexpr int kAccBufs = 3;      // accumulator ring in TMEM: tile i -> buffer i % 3
+constexpr int kTileBars = 6;     // per-tile barrier sets: tile i -> set i % 6 (see the barrier table)
+constexpr int kAccStride = 160;  // TMEM columns between accumulator buffers (>= largest UMMA N = 144)
 constexpr int kTmemCols = 512;
 
 // byte offset of 16-byte chunk c of row r inside a staging tile whose rows are bn_ch (64|128) bytes,
@@ -186,13 +209,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // barrier slots (8 bytes each)
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  // Per-tile barriers are indexed by tile % kTileBars (6 = lcm of the 3 accumulators and the 2 teams /
+  // MMA warps): an mbarrier wait only names a phase PARITY, so every barrier must always be waited on by
+  // the same party, which then sees each of its phases in turn.  Tile i uses accumulator i % 3.
   auto tfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + b); };
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 2 + b); };
-  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 4 + b); };
-  auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 4 + kMaxResBufs + b); };
-  const uint32_t bfull_bar = bar_base + 8u * (2 * kMaxStages + 4 + 2 * kMaxResBufs);  // resident B landed
-  volatile uint32_t *tmem_slot =
-      reinterpret_cast<volatile uint32_t *>(smem + sp.bar_off + 8 * (2 * kMaxStages + 5 + 2 * kMaxResBufs));
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + kTileBars + b); };
+  auto tstart_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 2 * kTileBars + b); };
+  auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + b); };
+  auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + kMaxResBufs + b); };
+  const uint32_t bfull_bar = bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs);  // resident B landed
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(
+      smem + sp.bar_off + 8 * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs + 1));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvGeom &g = a.g;
@@ -214,9 +241,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(tfull_bar(b), 1);
+    for (int b = 0; b < kTileBars; ++b) {
+      mbar_init(tfull_bar(b), (uint32_t)a.mma_warps_per_tile);
       mbar_init(tempty_bar(b), kTeam);
+      mbar_init(tstart_bar(b), 1);
     }
     for (int b = 0; b < sp.res_bufs; ++b) {
       mbar_init(rfull_bar(b), 1);
@@ -253,181 +281,194 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
 
   // ================================ TMA producers ===============================================
-  // Issuing one TMA box costs the issuing WARP ~250 (tiled) to ~420 (im2col) cycles and the lanes of a
-  // warp take turns (timeline: tools/trace_conv.py), so a single producer warp caps a K block at
-  // ~700-1300 cycles -- 2-4x the tensor time.  The loads are therefore spread over the three warps
-  // that have nothing else to do (0, 2 = TMEM allocator, 3):
-  //   A tiles   : warp 0, plus warp 2 when the weights are resident, plus warp 3 when there is no residual
-  //   B tiles   : warp 2 when weights are streamed (resident weights land once, issued by warp 0)
-  //   residual  : warp 3
-  // K blocks are dealt round-robin over (A warps x prod_lanes) issuers; each fills "its" stages and the
-  // MMA warp consumes them in order.
-  const int n_a_warps = 1 + (sp.b_resident ? 1 : 0) + (has_res ? 0 : 1);
-  int a_idx = -1;  // this warp's index among the A-producer warps
-  if (warp == 0) a_idx = 0;
-  else if (warp == 2 && sp.b_resident) a_idx = 1;
-  else if (warp == 3 && !has_res) a_idx = sp.b_resident ? 2 : 1;
-  const bool b_warp = warp == 2 && !sp.b_resident;
-  if (warp != 1 && warp < 4 && (a_idx >= 0 || b_warp)) {
-    const int L = a.prod_lanes;
-    if (lane < L) {
-      const uint32_t b_bytes = (uint32_t)(bn_cols * SWZ);
-      const uint32_t tx_bytes = (uint32_t)sp.a_bytes + (sp.b_resident ? 0u : b_bytes);
-      if (warp == 0 && sp.b_resident && walk.count > 0) {  // this CTA's n-tile never changes
-        if (lane == 0) mbar_expect_tx(bfull_bar, b_bytes * (uint32_t)a.num_kb);
-        for (int kb = lane; kb < a.num_kb; kb += L)
+  // What ONE warp can issue is the unit of throughput here (tools/issue_bench.cu, B200): a warp that
+  // walks a division-free loop in convergent code and lets one elected lane issue sustains one TMA box
+  // per ~300 cycles (tiled or im2col alike) and one tcgen05.mma per ~140 cycles (128-byte swizzle;
+  // ~260 with the 64-byte swizzle) WHATEVER the box size or the MMA's N; issuing from a divergent
+  // `if (lane == 0)` region instead makes the compiler wrap every such instruction in an
+  // ELECT / R2UR.BROADCAST loop that costs 2-4x more.  Different warps issue concurrently, so the four
+  // control warps are dealt as (SmemPlan::mma_warps == 1 frees warp 3 for a third producer):
+  //   warps 0 + 2 (+ 3) : producers; pipeline step c (a stage = sp.group K blocks of A, plus the B tile
+  //                       of the K block when weights are streamed) belongs to producer c % n_prod
+  //   warps 1 + 3       : MMA issuers; step c belongs to MMA warp c & 1
+  //   residual tiles    : warp 0, one box per tile, up to a tile ahead of the A tiles it is loading
+  //   resident weights  : land once, issued by warp 0
+  const int w_mma1 = sp.mma_warps == 2 ? 3 : -1;  // second MMA warp
+  const int n_a_warps = 2;
+  const int a_idx = warp == 0 ? 0 : (warp == 2 ? 1 : -1);
+  constexpr bool b_warp = false;
+  if (a_idx >= 0) {
+    const uint32_t b_bytes = (uint32_t)(bn_cols * SWZ);
+    const int grp = sp.group;
+    const uint32_t tx_bytes = (uint32_t)(grp * sp.a_bytes) + (sp.b_resident ? 0u : b_bytes);
+    if (warp == 0 && sp.b_resident && walk.count > 0) {  // this CTA's n-tile never changes
+      if (elect_one()) {
+        mbar_expect_tx(bfull_bar, b_bytes * (uint32_t)a.num_kb);
+        for (int kb = 0; kb < a.num_kb; ++kb)
           tma_load_2d(smem_base + sp.b_off + kb * sp.b_tile_bytes, &tmB, bfull_bar, kb * SWZ, walk.my_n * bn_cols);
       }
-      const int items = walk.count * a.num_kb;
-      int tn = 0;
-      const int tid_ = (b_warp ? 12 : a_idx * 4) + lane;
-      const int first = b_warp ? lane : a_idx + n_a_warps * lane;
-      const int step = b_warp ? L : n_a_warps * L;
-      // (i, kb) and the stage/phase advance incrementally; tile coordinates only when i changes
-      int i = first / a.num_kb, kb = first - i * a.num_kb;
-      int stage = first % sp.stages;
-      uint32_t phase = (uint32_t)((first / sp.stages) & 1);
-      const int step_i = step / a.num_kb, step_kb = step - step_i * a.num_kb;
-      const int step_st = step % sp.stages, step_ph = step / sp.stages;
-      int cur_i = -1, n_tile = 0, m0 = 0, cw = 0, chh = 0, cn = 0;
-      for (int c = first; c < items; c += step) {
-        if (i != cur_i) {
-          int m_tile;
-          walk.at(i, m_tile, n_tile);
-          m0 = m_tile * kTileM;
-          if (a.a_im2col && !b_warp) {
-            const int hw = g.Wo * g.Ho;
-            cn = m0 / hw;
-            const int rem = m0 - cn * hw;
-            const int p = rem / g.Wo;
-            cw = (rem - p * g.Wo) * g.stride - g.pad;
-            chh = p * g.stride - g.pad;
-          }
-          cur_i = i;
-        }
-        const uint32_t sa = smem_base + stage * sp.stage_bytes;
-        mbar_wait(empty_bar(stage), phase ^ 1);
-        if (b_warp) {  // the A issuer posts the stage's byte count; tx-count may run negative meanwhile
-          trace_ev(a, tid_, tn, 2, c);
-          tma_load_2d(sa + sp.a_bytes, &tmB, full_bar(stage), kb * SWZ, n_tile * bn_cols);
-          trace_ev(a, tid_, tn, 3, c);
-        } else {
-          trace_ev(a, tid_, tn, 0, c);
-          mbar_expect_tx(full_bar(stage), tx_bytes);
-          if (a.a_im2col) {
-            const int tap = kb / a.chunks_per_tap;
-            const int cchunk = kb - tap * a.chunks_per_tap;
-            const int r = tap / g.kw, sx = tap - r * g.kw;
-            tma_load_im2col_4d(sa, &tmA, full_bar(stage), cchunk * SWZ, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
-          } else {
-            tma_load_2d(sa, &tmA, full_bar(stage), kb * SWZ, m0);
-          }
-          trace_ev(a, tid_, tn, 1, c);
-        }
-        kb += step_kb; i += step_i;
-        if (kb >= a.num_kb) { kb -= a.num_kb; ++i; }
-        stage += step_st; phase ^= (uint32_t)(step_ph & 1);
-        if (stage >= sp.stages) { stage -= sp.stages; phase ^= 1; }
-      }
+      __syncwarp();
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ==============================================
-    // The WHOLE warp walks the loop (convergent, every operand warp-uniform, so the descriptors live
-    // in uniform registers) and one elected lane issues.  Issuing from inside an `if (lane == 0)`
-    // region instead makes the compiler wrap every tcgen05.mma in an ELECT/R2UR.BROADCAST loop:
-    // ~178 cycles per instruction whatever its N (tools/umma_bench.cu), i.e. 2.5x the tensor time.
+    const int ngrp = a.num_grp, cpt = a.chunks_per_tap;
+    const int items = walk.count * ngrp;
+    int tn = 0;
+    const int tid_ = b_warp ? 12 : a_idx * 4;
+    const int first = b_warp ? 0 : a_idx;
+    const int step = b_warp ? 1 : n_a_warps;  // <= 2 <= pipeline depth
+    // (tile i, step gi inside the tile) and the stage/phase advance incrementally; tile coordinates are
+    // recomputed only when i changes
+    int i = first / ngrp, gi = first - i * ngrp;
+    int stage = first % sp.stages;
+    uint32_t phase = (uint32_t)((first / sp.stages) & 1);
+    int cur_i = -1, n_tile = 0, m0 = 0, cw = 0, chh = 0, cn = 0;
+    const bool tracing = a.trace != nullptr;
+    // residual (block identity) tiles: a ring of res_bufs boxes, filled by warp 0
+    const bool res_warp = has_res && warp == 0;
+    const uint32_t res_bytes = (uint32_t)(kTileM * g.bn_ch);
+    int res_next = 0, res_buf = 0;
+    uint32_t res_ph = 0;
+    auto issue_residuals = [&](int upto) {  // residual boxes of tiles [res_next, upto]
+      for (; res_next <= upto && res_next < walk.count; ++res_next) {
+        int mt, nt;
+        walk.at(res_next, mt, nt);
+        mbar_wait(rempty_bar(res_buf), res_ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(rfull_bar(res_buf), res_bytes);
+          tma_load_2d(smem_base + sp.res_off + res_buf * kOutTileBytes, &tmR, rfull_bar(res_buf), nt * g.bn_ch,
+                      mt * kTileM);
+        }
+        __syncwarp();
+        if (++res_buf == sp.res_bufs) { res_buf = 0; res_ph ^= 1; }
+      }
+    };
+    for (int c = first; c < items; c += step) {
+      if (res_warp) issue_residuals(i + 1);
+      if (i != cur_i) {
+        int m_tile;
+        walk.at(i, m_tile, n_tile);
+        m0 = m_tile * kTileM;
+        if (a.a_im2col && !b_warp) {
+          const int hw = g.Wo * g.Ho;
+          cn = m0 / hw;
+          const int rem = m0 - cn * hw;
+          const int p = rem / g.Wo;
+          cw = (rem - p * g.Wo) * g.stride - g.pad;
+          chh = p * g.stride - g.pad;
+        }
+        cur_i = i;
+      }
+      const uint32_t sa = smem_base + stage * sp.stage_bytes;
+      const uint32_t fb = full_bar(stage);
+      const int kb0 = gi * grp;  // first K block of this step
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      if (tracing && lane == 0) trace_ev(a, tid_, tn, b_warp ? 2 : 0, c);
+      if (a.a_im2col) {
+        int tap = kb0 / cpt, cchunk = kb0 - tap * cpt;
+        if (elect_one()) {
+          mbar_expect_tx(fb, tx_bytes);
+          for (int j = 0; j < grp; ++j) {
+            const int r = g.kw == 3 ? (tap * 11) >> 5 : (g.kw == 1 ? tap : tap / g.kw);
+            const int sx = tap - r * g.kw;
+            tma_load_im2col_4d(sa + j * sp.a_bytes, &tmA, fb, cchunk * SWZ, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
+            if (++cchunk == cpt) { cchunk = 0; ++tap; }
+          }
+          if (!sp.b_resident) tma_load_2d(sa + sp.a_bytes, &tmB, fb, kb0 * SWZ, n_tile * bn_cols);
+        }
+      } else {
+        if (elect_one()) {
+          mbar_expect_tx(fb, tx_bytes);
+          for (int j = 0; j < grp; ++j) tma_load_2d(sa + j * sp.a_bytes, &tmA, fb, (kb0 + j) * SWZ, m0);
+          if (!sp.b_resident) tma_load_2d(sa + sp.a_bytes, &tmB, fb, kb0 * SWZ, n_tile * bn_cols);
+        }
+      }
+      __syncwarp();
+      if (tracing && lane == 0) trace_ev(a, tid_, tn, b_warp ? 3 : 1, c);
+      gi += step;
+      while (gi >= ngrp) { gi -= ngrp; ++i; }
+      stage += step;
+      if (stage >= sp.stages) { stage -= sp.stages; phase ^= 1; }
+    }
+    if (res_warp) issue_residuals(walk.count - 1);
+  } else if (warp == 1 || warp == w_mma1) {
+    // ================================ MMA issuers =============================================
+    // With two issuing warps, pipeline step c (counted over all the tiles of this CTA) belongs to warp
+    // c & 1 and both accumulate into the tile's TMEM buffer (integer accumulation commutes).  A single
+    // warp retires one tcgen05.mma per ~140 cycles whatever its N, i.e. half the tensor pipe at N = 144.
+    // Ordering inside a tile: the MMAs of its first step overwrite the accumulator, so the warp that
+    // does not own that step waits (tstart) until they have completed before its own first MMA; the
+    // accumulator goes to the epilogue (tfull) when BOTH warps' MMAs of the tile have completed.
+    // Each WHOLE warp walks the loop (convergent, every operand warp-uniform, so the descriptors live
+    // in uniform registers) and one elected lane issues.
     // instruction descriptor: D=s32, A=B=u8, both K-major, M=128, N=umma_n
+    const int w = warp == 1 ? 0 : 1;
+    const int nmw = sp.mma_warps;
     const uint32_t idesc = (2u << 4) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    // This warp's own instruction stream is what paces the small-K layers (one warp retires a
-    // dependent instruction every ~5 cycles), so everything that can be is carried incrementally:
-    // descriptor low words (smem address >> 4) per stage / resident B tile, barrier addresses, phase.
     const uint64_t desc_hi = make_smem_desc<SWZ>(0) & 0xffffffff00000000ull;
     const uint32_t desc_lo0 = (uint32_t)(make_smem_desc<SWZ>(0) & 0xffffffffull);  // flags of the low word
-    const uint32_t n_stages = (uint32_t)sp.stages, n_kb = (uint32_t)a.num_kb;
+    const int n_stages = sp.stages, ngrp = a.num_grp, grp = sp.group;
+    const int nw = a.mma_warps_per_tile;  // MMA warps that touch one tile
     const uint32_t stage16 = (uint32_t)sp.stage_bytes >> 4, a16 = (uint32_t)sp.a_bytes >> 4;
     const uint32_t btile16 = (uint32_t)sp.b_tile_bytes >> 4;
     const uint32_t a_lo_first = desc_lo0 | ((smem_base & 0x3FFFFu) >> 4);
     const uint32_t b_lo_first = desc_lo0 | (((smem_base + (uint32_t)sp.b_off) & 0x3FFFFu) >> 4);
     const bool resident = sp.b_resident != 0;
     const bool tracing = a.trace != nullptr;
-    uint32_t stage = 0, phase = 0;
-    uint32_t a_lo = a_lo_first, fbar = full_bar(0), ebar = empty_bar(0);
+    const int items = walk.count * ngrp;
     int tn = 0;
     if (resident && walk.count > 0) {
       mbar_wait(bfull_bar, 0);  // the CTA's weights are in shared memory
       tc_fence_after();
     }
-    for (int i = 0; i < walk.count; ++i) {
-      const int buf = i & 1;
-      const uint32_t acc_phase = (uint32_t)((i >> 1) & 1);
-      mbar_wait(tempty_bar(buf), acc_phase ^ 1);  // epilogue has drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_u + buf * kAccStride;
-      const uint32_t tbar = tfull_bar(buf);
-      uint32_t b_lo = b_lo_first;
-      // two K blocks per trip whenever both fit before the ring wraps: the two barrier polls, the
-      // descriptor moves and the issue overlap instead of forming one dependent chain per K block
-      for (uint32_t kb = 0; kb < n_kb;) {
-        const bool pair = kb + 1 < n_kb && stage + 1 < n_stages;
-        if (tracing && lane == 0) trace_ev(a, 16, tn, 7, i * a.num_kb + (int)kb);
-        const bool ok0 = mbar_try_wait(fbar, phase);
-        const bool ok1 = pair ? mbar_try_wait(fbar + 8, phase) : true;
-        if (!ok0) mbar_wait(fbar, phase);
-        if (!ok1) mbar_wait(fbar + 8, phase);
+    int i = w / ngrp, gi = w - i * ngrp;  // w < 2
+    int stage = w % n_stages;
+    uint32_t phase = (uint32_t)((w / n_stages) & 1);
+    int cur_i = -1, acc = 0, tb = 0;
+    for (int c = w; c < items; c += nmw) {
+      if (i != cur_i) {  // this warp's first step of tile i
+        cur_i = i;
+        acc = i % kAccBufs;
+        tb = i % kTileBars;
+        if (gi == 0) {  // the epilogue of tile i - 3 has drained this accumulator
+          if (i >= kAccBufs) mbar_wait(tempty_bar((i - kAccBufs) % kTileBars), (uint32_t)(((i - kAccBufs) / kTileBars) & 1));
+        } else {        // the overwriting MMAs of this tile have completed
+          mbar_wait(tstart_bar(tb), (uint32_t)((i / kTileBars) & 1));
+        }
         tc_fence_after();
-        if (tracing && lane == 0) trace_ev(a, 16, tn, 4, i * a.num_kb + (int)kb);
-        const uint64_t da0 = desc_hi | a_lo;
-        const uint64_t db0 = desc_hi | (resident ? b_lo : a_lo + a16);
-        const uint64_t da1 = desc_hi | (a_lo + stage16);
-        const uint64_t db1 = desc_hi | (resident ? b_lo + btile16 : a_lo + stage16 + a16);
-        if (elect_one()) {
+      }
+      const uint32_t tmem_d = tmem_u + acc * kAccStride;
+      const uint32_t a_lo = a_lo_first + (uint32_t)stage * stage16;
+      const uint32_t b_lo = resident ? b_lo_first + (uint32_t)(gi * grp) * btile16 : a_lo + a16;
+      const bool last_mine = gi + nmw >= ngrp;  // this warp's last step of the tile
+      if (tracing && lane == 0) trace_ev(a, 16 + 3 * w, tn, 7, c);
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (tracing && lane == 0) trace_ev(a, 16 + 3 * w, tn, 4, c);
+      if (elect_one()) {
+        for (int j = 0; j < grp; ++j) {
+          const uint64_t da = desc_hi | (a_lo + (uint32_t)j * a16), db = desc_hi | (b_lo + (uint32_t)j * btile16);
 #pragma unroll
           for (int k = 0; k < SWZ / 32; ++k)  // UMMA_K = 32 bytes of K per instruction
-            umma_i8(tmem_d, da0 + 2 * k, db0 + 2 * k, idesc, (kb | (uint32_t)k) != 0);
-          umma_commit(ebar);  // frees the smem slot when these MMAs retire
-          if (pair) {
-#pragma unroll
-            for (int k = 0; k < SWZ / 32; ++k) umma_i8(tmem_d, da1 + 2 * k, db1 + 2 * k, idesc, 1);
-            umma_commit(ebar + 8);
-          }
-          if (kb + (pair ? 2u : 1u) == n_kb) umma_commit(tbar);  // accumulator complete -> epilogue
+            umma_i8(tmem_d, da + 2 * k, db + 2 * k, idesc, (uint32_t)(gi | j | k) != 0u);
         }
-        __syncwarp();
-        const uint32_t adv = pair ? 2u : 1u;
-        kb += adv;
-        b_lo += adv * btile16;
-        a_lo += adv * stage16; fbar += 8 * adv; ebar += 8 * adv;
-        stage += adv;
-        if (stage == n_stages) {
-          stage = 0; phase ^= 1;
-          a_lo = a_lo_first; fbar = full_bar(0); ebar = empty_bar(0);
-        }
+        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+        if (gi == 0 && nw > 1) umma_commit(tstart_bar(tb));
+        if (last_mine) umma_commit(tfull_bar(tb));  // this warp's share of the accumulator is complete
       }
-    }
-  } else if (warp == 3) {
-    // ================================ residual producer (has_res: warp 3 is not an A warp) ====
-    if (has_res && lane < a.res_lanes) {
-      const uint32_t res_bytes = (uint32_t)(kTileM * g.bn_ch);
-      for (int it = lane; it < walk.count; it += a.res_lanes) {
-        int m_tile, n_tile;
-        walk.at(it, m_tile, n_tile);
-        const int buf = (int)(it % sp.res_bufs);
-        const uint32_t ph = (uint32_t)((it / sp.res_bufs) & 1);
-        mbar_wait(rempty_bar(buf), ph ^ 1);
-        mbar_expect_tx(rfull_bar(buf), res_bytes);
-        tma_load_2d(smem_base + sp.res_off + buf * kOutTileBytes, &tmR, rfull_bar(buf), n_tile * g.bn_ch,
-                    (int)(m_tile * kTileM));
-      }
+      __syncwarp();
+      gi += nmw;
+      while (gi >= ngrp) { gi -= ngrp; ++i; }
+      stage += nmw;
+      if (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================================ epilogue (2 teams of 8 warps) ============================
     constexpr bool kQuant = OUT == SLQ_OUT_U8 || OUT == SLQ_OUT_S8;
     constexpr int CW = W16 ? 16 : 32;              // accumulator columns per TMEM load
-    const int team = (warp - 4) >> 3;              // == accumulator buffer
+    const int team = (warp - 4) >> 3;              // tile i -> team i & 1
     const int half = ((warp - 4) >> 2) & 1;        // which half of the tile's channel units
     const int wq = warp & 3;                       // TMEM lane quarter this warp may touch
-    const int et = threadIdx.x - 128 - team * kTeam;  // 0..255 inside the team
+    const int et = threadIdx.x - 128 - team * kTeam;  // 0..255 inside the team (warps 4..19)
     const int row = wq * 32 + lane;                // tile row == TMEM lane
     ChanParam *prm = reinterpret_cast<ChanParam *>(smem + sp.prm_off) + team * 128;
     const uint32_t prm_s = smem_base + sp.prm_off + team * 128 * 16;
@@ -446,7 +487,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int it = team; it < walk.count; it += 2) {
       int m_tile, n_tile;
       walk.at(it, m_tile, n_tile);
-      const uint32_t ph = (uint32_t)((it >> 1) & 1);
+      const int acc = it % kAccBufs, tb = it % kTileBars;
+      const uint32_t ph = (uint32_t)((it / kTileBars) & 1);
       // staging tile free again? (the previous TMA store of this team has read it)
       if (a.tma_out && et == 0) tma_store_wait_read();
       named_bar_sync(1 + team, kTeam);
@@ -460,13 +502,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         last_n_tile = n_tile;
         named_bar_sync(1 + team, kTeam);
       }
-      mbar_wait(tfull_bar(team), ph);
+      mbar_wait(tfull_bar(tb), ph);
       tc_fence_after();
       if (a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 5, (int)it);
       const int rbuf = has_res ? (int)(it % sp.res_bufs) : 0;
       const uint32_t rsb = smem_base + sp.res_off + rbuf * kOutTileBytes;
       if (has_res) mbar_wait(rfull_bar(rbuf), (uint32_t)((it / sp.res_bufs) & 1));
-      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + team * kAccStride;
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride;
       const long long m = (long long)m_tile * kTileM + row;
       const bool valid = m < g.M;
       const uint32_t S_raw = tmem_ld1(trow + bn_cols);
@@ -537,7 +579,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       if (a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
-      mbar_arrive(tempty_bar(team));  // kTeam arrivals release the accumulator buffer
+      mbar_arrive(tempty_bar(tb));  // kTeam arrivals release the accumulator buffer
       if (has_res) mbar_arrive(rempty_bar(rbuf));
       if (a.tma_out) {
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -692,17 +734,13 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   a.e = e;
   a.sp = make_plan(c->g, SWZ, e.res != nullptr);
   const int grid = plan_grid(c->g, a.sp, sm_count());
-  // ONE issuing lane per producer warp: two lanes of a warp that sleep in mbarrier.try_wait on different
-  // barriers delay each other's wake-up by ~1.5k cycles (timeline: tools/trace_conv.py), while separate
-  // warps wake within ~100 cycles.  (An issuer may run at most one mbarrier phase ahead of the consumer
-  // -- parity waits alias two phases apart -- which holds because issuers <= pipeline depth.)
-  a.prod_lanes = 1;
-  a.res_lanes = 1;
   a.trace = g_trace;
   a.trace_cap = g_trace_cap;
   a.a_im2col = c->a_im2col;
   a.chunks_per_tap = c->g.Cin / SWZ;
   a.num_kb = c->g.kh * c->g.kw * a.chunks_per_tap;
+  a.num_grp = a.num_kb / a.sp.group;
+  a.mma_warps_per_tile = (a.sp.mma_warps == 2 && a.num_grp >= 2) ? 2 : 1;
   a.m_tiles = ceil_div(c->g.M, kTileM);
   a.tma_out = tma_out;
   conv_umma_kernel<SWZ, W16, OUT, RES><<<grid, kThreads, a.sp.total, st>>>(c->tmA, c->tmB, c->tmO, c->tmR, a);

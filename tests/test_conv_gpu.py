@@ -152,3 +152,42 @@ def test_umma_equals_simt_at_full_batch():
             assert np.array_equal(oa.astype(np.int64).sum(0), codes @ A_sum)
         a.close()
         b.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    # (cin, cout, k, stride, H, fp32 rows, mode, residual: 0 none / 1 u8 / 2 s8)
+    (64, 64, 1, 1, 56, False, "u8", 0),      # one K block per tile, many tiles per CTA
+    (64, 256, 1, 1, 56, False, "u8", 2),     # one K block, two n-tiles, signed residual
+    (64, 256, 1, 1, 56, True, "s8", 0),      # downsample: two-limb rows, signed output
+    (256, 64, 1, 1, 56, False, "u8", 0),     # two K blocks per tile
+    (64, 64, 3, 1, 56, False, "u8", 0),      # nine 64-byte K blocks
+    (256, 512, 1, 2, 56, True, "s8", 0),     # strided two-limb downsample
+    (128, 512, 1, 1, 28, False, "u8", 1),    # u8 residual, four n-tiles
+    (512, 512, 3, 1, 14, False, "u8", 0),    # streamed weights, 36 K blocks
+], ids=lambda c: "c%d-%d_k%d_s%d_h%d_%s_r%d" % (c[0], c[1], c[2], c[3], c[4], c[6], c[7]))
+def test_umma_equals_simt_epilogue_modes_multi_tile(cfg):
+    """Many tiles per CTA through every epilogue flavour the engine uses (u8 / s8 output, no / u8 / s8
+    residual, two-limb rows): tcgen05 output bytes == dp4a checker bytes."""
+    import slq_lib as L
+    cin, cout, k, stride, H, fp32_rows, mode, res_kind = cfg
+    N = 96  # >= 12 tiles per CTA: every barrier ring wraps more than once
+    bits = np.full(cout, 32, np.int32) if fp32_rows else _mixed_bits(cout, cin + k)
+    a = ConvCase(N, H, cin, cout, k, stride, bits, seed=4)
+    b = ConvCase(N, H, cin, cout, k, stride, bits, seed=4, impl=L.IMPL_SIMT)
+    rng = np.random.default_rng(9)
+    K = cin * k * k
+    wscale = (rng.uniform(0.5, 1.5, cout) / (K * 40.0 * (256.0 if fp32_rows else 1.0))).astype(np.float32)
+    zf = -rng.integers(100, 156, cout).astype(np.float32) * (256.0 if fp32_rows else 1.0)
+    bias = rng.normal(0, 0.5, cout).astype(np.float32)
+    scales = np.array([1.0, 1.0 / 64, 1.0 / 32, 1.0], np.float32)
+    res = None
+    if res_kind:
+        res = rng.integers(0, 256, (a.M, cout), dtype=np.uint8)
+    out_mode = L.OUT_U8 if mode == "u8" else L.OUT_S8
+    args = dict(res=res, res_id=2 if res_kind else -1, res_signed=1 if res_kind == 2 else 0, relu=1)
+    oa = a.run_epi(out_mode, wscale, zf, bias, scales, 0, 1, **args)
+    ob = b.run_epi(out_mode, wscale, zf, bias, scales, 0, 1, **args)
+    assert len(np.unique(oa)) > 8  # the parameters exercise the quantiser's range
+    assert np.array_equal(oa, ob)
+    a.close()
+    b.close()
