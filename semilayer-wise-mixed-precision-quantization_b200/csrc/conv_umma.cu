@@ -342,7 +342,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
     for (int c = first; c < items; c += step) {
-      if (res_warp) issue_residuals(i + 1);
+      if (res_warp) issue_residuals(i + sp.res_bufs - 3);  // never waits on a tile whose A tiles are not loaded yet
       if (i != cur_i) {
         int m_tile;
         walk.at(i, m_tile, n_tile);
