@@ -256,8 +256,13 @@ def main():
     sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(st)
-    for _ in range(args.steps):
-        step()
+    for i in range(args.steps):
+        if not use_graph and i == args.steps - 1:  # profiling hook: ncu --nvtx --nvtx-include "slq_step/"
+            torch.cuda.nvtx.range_push("slq_step")
+            step()
+            torch.cuda.nvtx.range_pop()
+        else:
+            step()
     e1.record(st)
     barrier()
     clocks = sampler.stop()
@@ -274,20 +279,25 @@ def main():
     # step's logits come back to the host (a blocking read), so nothing is deferred past the region.
     e2e_steps = max(3, min(args.steps, 20))
     copy_stream = torch.cuda.Stream(dev)
-    dbuf = [torch.empty_like(x), torch.empty_like(x)]
+    NB = 3  # input buffers: the copy engine always has the next batch queued behind the one in flight
+    dbuf = [torch.empty_like(x) for _ in range(NB)]
+    landed = [torch.cuda.Event() for _ in range(NB)]
 
     def fetch(i):  # host -> device copy of step i's input on the copy stream
         with torch.cuda.stream(copy_stream):
-            dbuf[i % 2].copy_(x_host, non_blocking=True)
+            dbuf[i % NB].copy_(x_host, non_blocking=True)
+            landed[i % NB].record(copy_stream)
 
     def e2e_loop(n):
         fetch(0)
+        if n > 1:
+            fetch(1)
         out = None
         for i in range(n):
-            st.wait_stream(copy_stream)       # step i's input has landed
-            if i + 1 < n:
-                fetch(i + 1)                  # dbuf[(i+1)%2] was last read by step i-1, which has finished
-            out = net(dbuf[i % 2]).cpu()      # forward + D2H of the logits (synchronises)
+            st.wait_event(landed[i % NB])     # step i's input has landed
+            if i + 2 < n:
+                fetch(i + 2)                  # dbuf[(i+2)%3] was last read by step i-1, which has finished
+            out = net(dbuf[i % NB]).cpu()     # forward + D2H of the logits (synchronises)
         return out
 
     e2e_loop(2)
@@ -370,7 +380,7 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps,
-                "overlap": "double-buffered pinned H2D on a copy stream; blocking D2H of the logits each step"},
+                "overlap": "pinned fp32 H2D two batches ahead on a copy stream; blocking D2H of the logits each step"},
         "gpu_launches": int(eng.kernel_launches * args.steps),
         "roofline": roofline,
         "pct_int8_peak_whole_net": 100.0 * (value / world) * GOP_PER_IMG[args.arch] * 1e9 / (int8_peak * 1e12),
