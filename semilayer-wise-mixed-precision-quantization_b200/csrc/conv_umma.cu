@@ -230,6 +230,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const TileWalk walk(a);
 
   // ---- one-time setup -----------------------------------------------------------------------
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may queue behind this one
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -309,6 +310,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       __syncwarp();
     }
+    grid_dependency_wait();  // activations of the previous layer (weights above are static)
     const int ngrp = a.num_grp, cpt = a.chunks_per_tap;
     const int items = walk.count * ngrp;
     int tn = 0;
@@ -463,6 +465,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ================================ epilogue (2 teams of 8 warps) ============================
+    grid_dependency_wait();  // before the first global write / residual read
     constexpr bool kQuant = OUT == SLQ_OUT_U8 || OUT == SLQ_OUT_S8;
     constexpr int CW = W16 ? 16 : 32;              // accumulator columns per TMEM load
     const int team = (warp - 4) >> 3;              // tile i -> team i & 1
@@ -743,8 +746,21 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   a.mma_warps_per_tile = (a.sp.mma_warps == 2 && a.num_grp >= 2) ? 2 : 1;
   a.m_tiles = ceil_div(c->g.M, kTileM);
   a.tma_out = tma_out;
-  conv_umma_kernel<SWZ, W16, OUT, RES><<<grid, kThreads, a.sp.total, st>>>(c->tmA, c->tmB, c->tmO, c->tmR, a);
-  SLQ_LAUNCH_CHECK();
+  // Programmatic dependent launch: this grid's CTAs may start (barrier / TMEM set-up, resident weights)
+  // on an SM as soon as the previous kernel's CTA there has exited; griddepcontrol.wait in the kernel
+  // holds everything that touches activations until the previous grid has completed.
+  static const bool pdl = getenv("SLQ_NO_PDL") == nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = (size_t)a.sp.total;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  SLQ_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<SWZ, W16, OUT, RES>, c->tmA, c->tmB, c->tmO, c->tmR, a));
   return SLQ_OK;
 }
 
