@@ -4,7 +4,7 @@ batch N in {1 .. 512}, and the weight quantizer per K x bit in {4, 8}; BASELINE.
 Per conv shape and batch: device time of ONE launch (CUDA events on the launching stream, best of
 `--reps` after a warm-up, a 256 MB L2 flush between repetitions), TOPS = 2*MAC / t, % of the INT8 tensor
 peak, algorithmic GB/s (u8 NHWC in + out + residual + weights once) and which roof is nearer.
-Per (K, bit): one slq_quantize_rows launch over 4096 rows, GB/s of algorithmic bytes (fp32 row read +
+Per (K, bit): one slq_quantize_rows launch over 128 MB of fp32 rows, GB/s of algorithmic bytes (fp32 row read +
 write-back + packed codes + 8 B metadata).
 
 usage (GPU box):  python tools/microbench.py [--arch resnet50] [--batches 1,8,32,128,256,512] [--out FILE.json]
@@ -98,11 +98,11 @@ def main():
         net._slq_engines = {}
         torch.cuda.empty_cache()
 
-    # ---- quantizer: one launch over 4096 rows per (K, bit) --------------------------------------
+    # ---- quantizer: one launch over 128 MB of rows per (K, bit) ----------------------------------
     print("\n%-6s %4s %9s %9s %7s" % ("K", "bit", "us", "GB/s", "%hbm"))
     lib = L.lib()
-    rows_n = 4096
     for K in (64, 128, 256, 512, 576, 1024, 1152, 2048, 2304, 4608):
+        rows_n = (1 << 25) // K  # 128 MB of fp32 rows per launch: larger than L2, long enough to time
         for bit in (4, 8):
             w = torch.randn(rows_n, K, device=dev)
             rows = torch.arange(rows_n, dtype=torch.int32, device=dev)
