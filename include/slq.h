@@ -200,6 +200,17 @@ SLQ_API int slq_stem_set_weights(slq_stem *s, const float *w, void *stream);
 SLQ_API int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, const float *bn_b,
                             const float *act_scales, int32_t out_id, void *out, int32_t out_mode,
                             float *f32_scratch, void *stream);
+/* The same launch for the other element types a loader may hand over (the data format on the host side
+ * of the path, imagenet.py:14-40): SLQ_IN_F16 = the fp32 image already rounded to fp16 (the stem rounds
+ * its operands to fp16 anyway, so the logits are bit-identical to the fp32 call); SLQ_IN_U8 = raw pixels,
+ * normalised on the fly exactly as torchvision's ToTensor + Normalize (imagenet.py:14-15):
+ * (u8 / 255 - mean[c]) / std[c] in fp32; `norm` = HOST floats {mean[3], std[3]} (SLQ_IN_U8 only).     */
+#define SLQ_IN_F32 0
+#define SLQ_IN_F16 1
+#define SLQ_IN_U8 2
+SLQ_API int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, const float *norm,
+                               const float *bn_a, const float *bn_b, const float *act_scales, int32_t out_id,
+                               void *out, int32_t out_mode, float *f32_scratch, void *stream);
 
 /* Tail: resnet.py:216-218  adaptive_avg_pool2d((1,1)) + flatten + fc (fp32 weights + bias).
  * x u8 NHWC [N, HW, C] -> logits fp32 [N, O]; pooled is scratch [N, C] fp32.                     */

@@ -76,7 +76,8 @@ __global__ void stem_weights_kernel(const float *__restrict__ w, __half *__restr
 }
 
 struct StemArgs {
-  const float *x;
+  const void *x;       // [N,3,H,W]: fp32 | fp16 | u8 (slq_stem_launch_in)
+  float nmean[3], nstd[3];  // u8 input: value = (u/255 - mean[c]) / std[c]  (imagenet.py:14-15 ToTensor + Normalize)
   int N, H, W, Hc, Wc, Hp, Wp;
   const __half *wh;
   const float *bn_a, *bn_b, *act_scales;
@@ -102,10 +103,27 @@ __device__ __forceinline__ void stem_trace(const StemArgs &a, int issuer, int &n
 
 // A load whose ISSUE POINT the compiler must keep: __ldg() is an invariant load that gets sunk to its
 // first use (after the A-tile build), which exposes the whole DRAM latency once per conv row.
-__device__ __forceinline__ float ldg_pinned(const float *p) {
-  float v;
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+// IN selects the element type of the image in HBM (SLQ_IN_*); the value is returned RAW (fp32 bits, fp16
+// bits or the byte) and turned into the fp32 pixel by stem_pixel() after the build, so that only the
+// load itself is pinned.
+template <int IN>
+__device__ __forceinline__ uint32_t ldg_pinned(const void *base, long long idx) {
+  uint32_t v;
+  if (IN == SLQ_IN_F32) asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const float *>(base) + idx) : "memory");
+  else if (IN == SLQ_IN_F16) {
+    uint16_t h;
+    asm volatile("ld.global.nc.b16 %0, [%1];" : "=h"(h) : "l"(reinterpret_cast<const uint16_t *>(base) + idx) : "memory");
+    v = h;
+  } else asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(reinterpret_cast<const uint8_t *>(base) + idx) : "memory");
   return v;
+}
+// raw element -> the fp32 pixel value the reference's model would see (then rounded to fp16 by the caller)
+template <int IN>
+__device__ __forceinline__ float stem_pixel(uint32_t raw, float mean, float stdv) {
+  if (IN == SLQ_IN_F32) return __uint_as_float(raw);
+  if (IN == SLQ_IN_F16) return __half2float(__ushort_as_half((unsigned short)raw));
+  // torchvision ToTensor: u8 -> fp32 / 255 ; Normalize: (t - mean) / std -- three separately rounded fp32 ops
+  return __fdiv_rn(__fsub_rn(__fdiv_rn((float)raw, 255.0f), mean), stdv);
 }
 
 // conv rows [p0, p1) of unit u and the pooled rows [j0, j1) it owns
@@ -136,6 +154,7 @@ __device__ __forceinline__ void stem_build_chunks(const __half *ring_q, uint8_t 
   }
 }
 
+template <int IN>
 __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -202,9 +221,9 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
-      const float *xn = a.x + (long long)n * 3 * a.H * a.W;
+      const long long xn = (long long)n * 3 * a.H * a.W;  // element index of image n
       // rows [lo, hi) of the image (may be outside: zeros) -> ring, through registers
-      auto load_rows = [&](int lo, int hi, float (&v)[kMaxPer], bool first) {
+      auto load_rows = [&](int lo, int hi, uint32_t (&v)[kMaxPer], bool first) {
         const int per_row = 3 * a.W;
         const int total = (hi - lo) * per_row;
         if (first) {  // unit start: 7 rows at once, written straight away
@@ -212,7 +231,9 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
             const int ri = e / per_row, rem = e - ri * per_row;
             const int c = rem / a.W, w = rem - c * a.W;
             const int h = lo + ri;
-            const float f = (h >= 0 && h < a.H) ? __ldg(xn + ((long long)c * a.H + h) * a.W + w) : 0.f;
+            const float f = (h >= 0 && h < a.H)
+                                ? stem_pixel<IN>(ldg_pinned<IN>(a.x, xn + ((long long)c * a.H + h) * a.W + w), a.nmean[c], a.nstd[c])
+                                : 0.f;
             ring[(((h + 16) & (kSfRing - 1)) * 3 + c) * kSfRowP + w + 3] = __float2half_rn(f);
           }
           return;
@@ -220,19 +241,21 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
         // steady state: thread = (one of the two new rows, one column), three channels: no divisions
         const int h = lo + lrow;
         const bool ok = lt < a.W && lrow < hi - lo && h >= 0 && h < a.H;
-        const float *src = xn + (long long)h * a.W + lt;
+        const long long src = xn + (long long)h * a.W + lt;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c] = ok ? ldg_pinned(src + (long long)c * a.H * a.W) : 0.f;
+        for (int c = 0; c < 3; ++c) v[c] = ok ? ldg_pinned<IN>(a.x, src + (long long)c * a.H * a.W) : 0u;
       };
-      auto store_rows = [&](int lo, int hi, const float (&v)[kMaxPer]) {
+      auto store_rows = [&](int lo, int hi, const uint32_t (&v)[kMaxPer]) {
         const int h = lo + lrow;
+        const bool inside = h >= 0 && h < a.H;  // rows outside the image are the conv's zero padding
         if (lt < a.W && lrow < hi - lo) {
           __half *dst = ring + ((h + 16) & (kSfRing - 1)) * 3 * kSfRowP + lt + 3;
 #pragma unroll
-          for (int c = 0; c < 3; ++c) dst[c * kSfRowP] = __float2half_rn(v[c]);
+          for (int c = 0; c < 3; ++c)
+            dst[c * kSfRowP] = __float2half_rn(inside ? stem_pixel<IN>(v[c], a.nmean[c], a.nstd[c]) : 0.f);
         }
       };
-      float nxt[kMaxPer];
+      uint32_t nxt[kMaxPer];
       named_bar_sync(1, kSfBuilders);  // nobody still builds from the previous unit's rows
       load_rows(2 * p0 - 3, 2 * p0 + 4, nxt, true);
       named_bar_sync(1, kSfBuilders);
@@ -418,7 +441,11 @@ extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace,
   s->num_ctas = (int)std::min<long long>((long long)N * units_per_img, sm_count());
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel<SLQ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stem_fused_kernel<SLQ_IN_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stem_fused_kernel<SLQ_IN_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
     if (e != cudaSuccess) {
       delete s;
       set_error("slq_stem_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -442,13 +469,25 @@ extern "C" int slq_stem_set_weights(slq_stem *s, const float *w, void *stream) {
 extern "C" int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, const float *bn_b,
                                const float *act_scales, int32_t out_id, void *out, int32_t out_mode,
                                float *f32_scratch, void *stream) {
+  return slq_stem_launch_in(s, x, SLQ_IN_F32, nullptr, bn_a, bn_b, act_scales, out_id, out, out_mode, f32_scratch, stream);
+}
+
+extern "C" int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, const float *norm, const float *bn_a,
+                                  const float *bn_b, const float *act_scales, int32_t out_id, void *out,
+                                  int32_t out_mode, float *f32_scratch, void *stream) {
   SLQ_CHECK_ARG(s && x && bn_a && bn_b && out, "slq_stem_launch: null pointer argument");
+  SLQ_CHECK_ARG(in_kind == SLQ_IN_F32 || in_kind == SLQ_IN_F16 || in_kind == SLQ_IN_U8, "slq_stem_launch: in_kind %d", in_kind);
+  SLQ_CHECK_ARG(in_kind != SLQ_IN_U8 || norm != nullptr, "slq_stem_launch: u8 input needs norm = {mean[3], std[3]}");
   SLQ_CHECK_ARG(out_mode == SLQ_OUT_U8 || out_mode == SLQ_OUT_F32, "slq_stem_launch: out_mode %d", out_mode);
   SLQ_CHECK_ARG(out_mode == SLQ_OUT_U8 ? act_scales != nullptr : f32_scratch != nullptr,
                 "slq_stem_launch: act_scales (u8) / f32_scratch (fp32) required");
   cudaStream_t st = (cudaStream_t)stream;
   StemArgs a;
   a.x = x;
+  for (int c = 0; c < 3; ++c) {
+    a.nmean[c] = in_kind == SLQ_IN_U8 ? norm[c] : 0.f;
+    a.nstd[c] = in_kind == SLQ_IN_U8 ? norm[3 + c] : 1.f;
+  }
   a.N = s->N; a.H = s->H; a.W = s->W; a.Hc = s->Hc; a.Wc = s->Wc; a.Hp = s->Hp; a.Wp = s->Wp;
   a.wh = s->wh;
   a.bn_a = bn_a; a.bn_b = bn_b; a.act_scales = act_scales; a.out_id = out_id; a.out_mode = out_mode;
@@ -462,7 +501,9 @@ extern "C" int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, c
     const char *d = getenv("SLQ_STEM_DBG");
     a.dbg = d ? atoi(d) : 0;
   }
-  stem_fused_kernel<<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
+  if (in_kind == SLQ_IN_F32) stem_fused_kernel<SLQ_IN_F32><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
+  else if (in_kind == SLQ_IN_F16) stem_fused_kernel<SLQ_IN_F16><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
+  else stem_fused_kernel<SLQ_IN_U8><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   SLQ_LAUNCH_CHECK();
   if (out_mode == SLQ_OUT_F32)
     return launch_stem_pool(f32_scratch, s->N, s->Hc, s->Wc, s->Hp, s->Wp, act_scales, out_id, out, SLQ_OUT_F32, st);

@@ -16,6 +16,7 @@ DIV_TRUE, DIV_RECIP = 0, 1
 IMPL_UMMA, IMPL_SIMT = 0, 1
 A_AUTO, A_IM2COL, A_TILED = 0, 1, 2
 OUT_U8, OUT_F32, OUT_ACC, OUT_S8 = 0, 1, 2, 3
+IN_F32, IN_F16, IN_U8 = 0, 1, 2  # element type of the image handed to the stem (slq_stem_launch_in)
 
 _i32, _i64, _vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_void_p
 
@@ -54,6 +55,7 @@ SIGNATURES = {
     "slq_stem_destroy": (None, [_vp]),
     "slq_stem_set_weights": (ctypes.c_int, [_vp, _vp, _vp]),
     "slq_stem_launch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "slq_stem_launch_in": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
     "slq_tail_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "slq_absmax_scale": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "slq_quantize_act": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),

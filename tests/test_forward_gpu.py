@@ -170,3 +170,24 @@ def test_tensor_core_stem_matches_exact_fp32_stem():
         assert abs(res["umma"][2] - res["simt"][2]) <= 1e-3 * res["simt"][2]
         d = (res["umma"][1].int() - res["simt"][1].int()).abs()
         assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.05
+
+
+def test_u8_and_fp16_inputs_give_the_fp32_logits_bit_for_bit():
+    """The loader-side data formats (reference imagenet.py:14-40): raw u8 pixels normalised inside the stem
+    kernel == the reference's CPU ToTensor + Normalize followed by the fp32 call, and the fp32 batch rounded
+    to fp16 == the fp32 call (the stem rounds its operands to fp16 anyway): identical logits, bit for bit."""
+    import imagenet
+    net = build_p0_model("resnet18", "cuda")
+    net.input_norm = (imagenet.MEAN, imagenet.STD)
+    (x_u8, _y), = imagenet.synthetic_loader(1, 5, 224, seed=7, dtype=torch.uint8)
+    x32 = imagenet.normalize_u8(x_u8)  # CPU, like the reference's DataLoader workers
+    ref = net(x32.cuda()).cpu().numpy()  # calibrates the engine on this batch
+    got_u8 = net(x_u8.cuda()).cpu().numpy()
+    got_f16 = net(x32.half().cuda()).cpu().numpy()
+    assert np.isfinite(ref).all() and np.abs(ref).max() > 0
+    assert np.array_equal(got_u8.view(np.uint32), ref.view(np.uint32))
+    assert np.array_equal(got_f16.view(np.uint32), ref.view(np.uint32))
+    # and a u8 batch without the normalisation constants is an error, not a guess
+    del net.input_norm
+    with pytest.raises(ValueError):
+        net(x_u8.cuda())

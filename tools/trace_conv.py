@@ -1,5 +1,5 @@
 """tools/trace_conv.py -- prints CTA 0's producer / MMA / epilogue timeline of one conv layer
-(slq_debug_set_trace).  usage: python tools/trace_conv.py cin cout k stride H [N]"""
+(slq_debug_set_trace).  usage: python tools/trace_conv.py cin cout k stride H [N [w16]]"""
 import ctypes
 import os
 import sys
@@ -16,7 +16,7 @@ from helpers import ConvCase  # noqa: E402
 
 cin, cout, k, stride, H = [int(v) for v in sys.argv[1:6]]
 N = int(sys.argv[6]) if len(sys.argv) > 6 else 256
-bits = np.full(cout, 8, np.int32)
+bits = np.full(cout, 32 if (len(sys.argv) > 7 and sys.argv[7] == 'w16') else 8, np.int32)
 case = ConvCase(N, H, cin, cout, k, stride, bits, seed=1)
 lib = L.lib()
 cap = 24 * 600
