@@ -75,7 +75,11 @@ def quantize_rows(tensor, rows, bits, write_back=True, want_codes=True, div_mode
     if bits_h.size and (bits_h.min() < 1 or bits_h.max() > 8):
         raise ValueError("bit-width must be in 1..8")
     n_jobs = rows_h.size
-    sizes = np.array([(lib.slq_packed_row_bytes(K, int(b)) + 15) // 16 * 16 for b in bits_h], np.int64)
+    # slq_packed_row_bytes for every job at once (a ctypes call per row would dominate a whole-model pass):
+    # 4-bit rows pack two codes per byte, 2-bit rows four, everything else up to 8 bits one
+    b64 = bits_h.astype(np.int64)
+    sizes = np.where(b64 == 4, (K + 1) // 2, np.where(b64 == 2, (K + 3) // 4, K))
+    sizes = (sizes + 15) // 16 * 16
     offs_h = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64) if n_jobs else np.zeros(0, np.int64)
     total = int(sizes.sum())
     dm = _div_mode_for(tensor, div_mode)
@@ -85,9 +89,11 @@ def quantize_rows(tensor, rows, bits, write_back=True, want_codes=True, div_mode
     if tensor.is_cuda:
         dev = tensor.device
         with torch.cuda.device(dev):
-            rows_d = torch.from_numpy(rows_h).to(dev)
-            bits_d = torch.from_numpy(bits_h).to(dev)
-            offs_d = torch.from_numpy(offs_h).to(dev)
+            # job table in ONE host->device copy: offsets (int64) | rows | bits (int32)
+            table = np.concatenate([offs_h.view(np.int32), rows_h, bits_h])
+            table_d = torch.from_numpy(table).to(dev)
+            offs_d = table_d[:2 * n_jobs].view(torch.int64)
+            rows_d, bits_d = table_d[2 * n_jobs:3 * n_jobs], table_d[3 * n_jobs:]
             blob = torch.empty(max(total, 16), dtype=torch.uint8, device=dev) if want_codes else None
             z = torch.empty(n_jobs, dtype=torch.int32, device=dev)
             s32 = torch.empty(n_jobs, dtype=torch.float32, device=dev)
