@@ -27,6 +27,10 @@ PKG = os.path.join(ROOT, "semilayer-wise-mixed-precision-quantization_b200")
 sys.path.insert(0, PKG)
 
 METRIC = "ResNet-50 mixed 8/4-bit images/s"
+
+
+def metric_name(arch):  # BASELINE.json's metric; the other architectures are parity / side configurations
+    return METRIC.replace("ResNet-50", {"resnet18": "ResNet-18", "resnet34": "ResNet-34"}.get(arch, "ResNet-50"))
 UNIT = "images/s"
 GOP_PER_IMG = {"resnet50": 8.178, "resnet34": 7.328, "resnet18": 3.628}  # 2*MAC, convs + fc
 ALGO_MB_PER_IMG = {"resnet50": 27.84, "resnet34": 9.17, "resnet18": 6.22}
@@ -130,7 +134,7 @@ def run_reference(args):
     total = sum(times)
     val = batch * len(times) / total
     line = {
-        "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "metric": metric_name(args.arch), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
         "config": {"workload": "%s semilayer 8/4-bit (P0) inference, synthetic 224x224, random-init" % args.arch,
@@ -393,7 +397,7 @@ def main():
                 "conv_ms_per_step_serialised": conv_ms, "step_ms": ms / args.steps}
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(args.arch), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic", "impl": "ours",
         "config": {"workload": "%s semilayer 8/4-bit (P0: %d of %d channels 4-bit) inference, batch %d per GPU, "
