@@ -135,8 +135,16 @@ struct KernelArgs {
 // debug timeline (CTA 0 only): every issuer owns a private region of the buffer, so logging is one
 // fire-and-forget store (no atomics: their latency would distort the very thing being measured)
 constexpr int kTraceIssuers = 24;
+// trace_cap < 0 selects "wait statistics only": every role adds up the cycles it spends blocked in its
+// mbarrier waits and CTA 0 writes one total per role at the end (slot = role) -- no per-step overhead
+__device__ __forceinline__ void mbar_wait_stat(uint32_t bar, uint32_t parity, long long &sum, bool stats) {
+  if (!stats) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();  // try_wait itself may suspend the thread: time the whole wait
+  mbar_wait(bar, parity);
+  sum += clock64() - t0;
+}
 __device__ __forceinline__ void trace_ev(const KernelArgs &a, int issuer, int &n, int ev, int idx) {
-  if (a.trace == nullptr || blockIdx.x != 0) return;
+  if (a.trace == nullptr || a.trace_cap < 0 || blockIdx.x != 0) return;
   const int per = a.trace_cap / kTraceIssuers;
   if (n < per) {
     long long *p = a.trace + 3LL * (issuer * per + n);
@@ -221,7 +229,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(
       smem + sp.bar_off + 8 * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs + 1));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the control loops
+  // (stage / barrier / descriptor arithmetic, branches) on the uniform datapath instead of R2UR-ing every
+  // TMA / MMA operand out of vector registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const ConvGeom &g = a.g;
   const EpiDev &e = a.e;
   const int bn_cols = g.bn_cols;
@@ -231,6 +242,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   // ---- one-time setup -----------------------------------------------------------------------
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the next kernel may queue behind this one
+  const long long t_entry = clock64();
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -314,16 +326,28 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ngrp = a.num_grp, cpt = a.chunks_per_tap;
     const int items = walk.count * ngrp;
     int tn = 0;
-    const int tid_ = b_warp ? 12 : a_idx * 4;
-    const int first = b_warp ? 0 : a_idx;
-    const int step = b_warp ? 1 : n_a_warps;  // <= 2 <= pipeline depth
-    // (tile i, step gi inside the tile) and the stage/phase advance incrementally; tile coordinates are
-    // recomputed only when i changes
+    const int tid_ = a_idx * 4;
+    const int first = a_idx;
+    constexpr int step = 2;  // two producer warps; the pipeline depth is even
+    // Everything a step needs is carried incrementally (a warp's control code runs at 5-10 cycles per
+    // dependent instruction: ~100 instructions per step were the bottleneck of the K-heavy layers):
+    //   (tile i, step gi inside the tile), first K block kb0 = gi * grp, its filter tap (tap_r, tap_s) and
+    //   channel chunk, the stage's shared-memory address / barrier / phase; tile coordinates and the tap
+    //   state are recomputed (with divisions) only when the tile changes.
     int i = first / ngrp, gi = first - i * ngrp;
     int stage = first % sp.stages;
     uint32_t phase = (uint32_t)((first / sp.stages) & 1);
+    uint32_t sa = smem_base + (uint32_t)(stage * sp.stage_bytes);
+    const uint32_t sa_step = (uint32_t)(step * sp.stage_bytes), sa_end = smem_base + (uint32_t)(sp.stages * sp.stage_bytes);
     int cur_i = -1, n_tile = 0, m0 = 0, cw = 0, chh = 0, cn = 0;
-    const bool tracing = a.trace != nullptr;
+    int kb0 = 0, tap_r = 0, tap_s = 0, cchunk = 0;
+    const int kb_step = step * grp;
+    const bool tracing = a.trace != nullptr && a.trace_cap >= 0;
+    const bool stats = a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0;
+    long long wsum = 0;
+    const long long tstart_clk = clock64();
+    const bool im2col = a.a_im2col != 0, streamed = !sp.b_resident;
+    const int kw = g.kw;
     // residual (block identity) tiles: a ring of res_bufs boxes, filled by warp 0
     const bool res_warp = has_res && warp == 0;
     const uint32_t res_bytes = (uint32_t)(kTileM * g.bn_ch);
@@ -344,53 +368,58 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     };
     for (int c = first; c < items; c += step) {
-      if (res_warp) issue_residuals(i + sp.res_bufs - 3);  // never waits on a tile whose A tiles are not loaded yet
-      if (i != cur_i) {
+      if (i != cur_i) {  // new tile: coordinates and tap state from scratch
+        if (res_warp) issue_residuals(i + sp.res_bufs - 3);  // never waits on a tile whose A tiles are not loaded yet
         int m_tile;
         walk.at(i, m_tile, n_tile);
         m0 = m_tile * kTileM;
-        if (a.a_im2col && !b_warp) {
+        kb0 = gi * grp;
+        if (im2col) {
           const int hw = g.Wo * g.Ho;
           cn = m0 / hw;
           const int rem = m0 - cn * hw;
           const int p = rem / g.Wo;
           cw = (rem - p * g.Wo) * g.stride - g.pad;
           chh = p * g.stride - g.pad;
+          const int tap = kb0 / cpt;
+          cchunk = kb0 - tap * cpt;
+          tap_r = tap / kw;
+          tap_s = tap - tap_r * kw;
         }
         cur_i = i;
       }
-      const uint32_t sa = smem_base + stage * sp.stage_bytes;
       const uint32_t fb = full_bar(stage);
-      const int kb0 = gi * grp;  // first K block of this step
-      mbar_wait(empty_bar(stage), phase ^ 1);
-      if (tracing && lane == 0) trace_ev(a, tid_, tn, b_warp ? 2 : 0, c);
-      if (a.a_im2col) {
-        int tap = kb0 / cpt, cchunk = kb0 - tap * cpt;
-        if (elect_one()) {
-          mbar_expect_tx(fb, tx_bytes);
+      mbar_wait_stat(empty_bar(stage), phase ^ 1, wsum, stats);
+      if (tracing && lane == 0) trace_ev(a, tid_, tn, 0, c);
+      if (elect_one()) {
+        mbar_expect_tx(fb, tx_bytes);
+        if (im2col) {
+          int cc = cchunk, ts = tap_s, tr = tap_r;
           for (int j = 0; j < grp; ++j) {
-            const int r = g.kw == 3 ? (tap * 11) >> 5 : (g.kw == 1 ? tap : tap / g.kw);
-            const int sx = tap - r * g.kw;
-            tma_load_im2col_4d(sa + j * sp.a_bytes, &tmA, fb, cchunk * SWZ, cw, chh, cn, (uint16_t)sx, (uint16_t)r);
-            if (++cchunk == cpt) { cchunk = 0; ++tap; }
+            tma_load_im2col_4d(sa + j * sp.a_bytes, &tmA, fb, cc * SWZ, cw, chh, cn, (uint16_t)ts, (uint16_t)tr);
+            if (++cc == cpt) { cc = 0; if (++ts == kw) { ts = 0; ++tr; } }
           }
-          if (!sp.b_resident) tma_load_2d(sa + sp.a_bytes, &tmB, fb, kb0 * SWZ, n_tile * bn_cols);
-        }
-      } else {
-        if (elect_one()) {
-          mbar_expect_tx(fb, tx_bytes);
+        } else {
           for (int j = 0; j < grp; ++j) tma_load_2d(sa + j * sp.a_bytes, &tmA, fb, (kb0 + j) * SWZ, m0);
-          if (!sp.b_resident) tma_load_2d(sa + sp.a_bytes, &tmB, fb, kb0 * SWZ, n_tile * bn_cols);
         }
+        if (streamed) tma_load_2d(sa + sp.a_bytes, &tmB, fb, kb0 * SWZ, n_tile * bn_cols);
       }
       __syncwarp();
-      if (tracing && lane == 0) trace_ev(a, tid_, tn, b_warp ? 3 : 1, c);
+      if (tracing && lane == 0) trace_ev(a, tid_, tn, 1, c);
+      // advance by `step` pipeline steps
       gi += step;
-      while (gi >= ngrp) { gi -= ngrp; ++i; }
-      stage += step;
-      if (stage >= sp.stages) { stage -= sp.stages; phase ^= 1; }
+      kb0 += kb_step;
+      if (gi >= ngrp) {
+        do { gi -= ngrp; ++i; } while (gi >= ngrp);  // tile change: state is rebuilt at the top of the loop
+      } else if (im2col) {
+        cchunk += kb_step;
+        while (cchunk >= cpt) { cchunk -= cpt; if (++tap_s == kw) { tap_s = 0; ++tap_r; } }
+      }
+      stage += step; sa += sa_step;
+      if (stage >= sp.stages) { stage -= sp.stages; sa -= sa_end - smem_base; phase ^= 1; }
     }
     if (res_warp) issue_residuals(walk.count - 1);
+    if (stats && lane == 0) { a.trace[a_idx] = wsum; a.trace[8 + a_idx] = clock64() - tstart_clk; if (a_idx == 0) a.trace[14] = tstart_clk - t_entry; }
   } else if (warp == 1 || warp == w_mma1) {
     // ================================ MMA issuers =============================================
     // With two issuing warps, pipeline step c (counted over all the tiles of this CTA) belongs to warp
@@ -415,7 +444,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t a_lo_first = desc_lo0 | ((smem_base & 0x3FFFFu) >> 4);
     const uint32_t b_lo_first = desc_lo0 | (((smem_base + (uint32_t)sp.b_off) & 0x3FFFFu) >> 4);
     const bool resident = sp.b_resident != 0;
-    const bool tracing = a.trace != nullptr;
+    const bool tracing = a.trace != nullptr && a.trace_cap >= 0;
+    const bool stats = a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0;
+    long long wfull = 0, wacc = 0;
+    const long long tstart_clk = clock64();
     const int items = walk.count * ngrp;
     int tn = 0;
     if (resident && walk.count > 0) {
@@ -432,9 +464,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         acc = i % kAccBufs;
         tb = i % kTileBars;
         if (gi == 0) {  // the epilogue of tile i - 3 has drained this accumulator
-          if (i >= kAccBufs) mbar_wait(tempty_bar((i - kAccBufs) % kTileBars), (uint32_t)(((i - kAccBufs) / kTileBars) & 1));
+          if (i >= kAccBufs) mbar_wait_stat(tempty_bar((i - kAccBufs) % kTileBars), (uint32_t)(((i - kAccBufs) / kTileBars) & 1), wacc, stats);
         } else {        // the overwriting MMAs of this tile have completed
-          mbar_wait(tstart_bar(tb), (uint32_t)((i / kTileBars) & 1));
+          mbar_wait_stat(tstart_bar(tb), (uint32_t)((i / kTileBars) & 1), wacc, stats);
         }
         tc_fence_after();
       }
@@ -443,7 +475,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t b_lo = resident ? b_lo_first + (uint32_t)(gi * grp) * btile16 : a_lo + a16;
       const bool last_mine = gi + nmw >= ngrp;  // this warp's last step of the tile
       if (tracing && lane == 0) trace_ev(a, 16 + 3 * w, tn, 7, c);
-      mbar_wait(full_bar(stage), phase);
+      mbar_wait_stat(full_bar(stage), phase, wfull, stats);
       tc_fence_after();
       if (tracing && lane == 0) trace_ev(a, 16 + 3 * w, tn, 4, c);
       if (elect_one()) {
@@ -463,6 +495,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       stage += nmw;
       if (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
     }
+    if (stats && lane == 0) { a.trace[2 + w] = wfull; a.trace[4 + w] = wacc; a.trace[10 + w] = clock64() - tstart_clk; }
   } else if (warp >= 4) {
     // ================================ epilogue (2 teams of 8 warps) ============================
     grid_dependency_wait();  // before the first global write / residual read
@@ -491,6 +524,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int u0 = half * (units >> 1), u1 = u0 + (units >> 1);
     int last_n_tile = -1;
     int tn = 0;
+    long long wepi = 0;
+    const long long tstart_clk = clock64();
     for (int it = team; it < walk.count; it += 2) {
       int m_tile, n_tile;
       walk.at(it, m_tile, n_tile);
@@ -509,7 +544,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         last_n_tile = n_tile;
         named_bar_sync(1 + team, kTeam);
       }
-      mbar_wait(tfull_bar(tb), ph);
+      mbar_wait_stat(tfull_bar(tb), ph, wepi, a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0);
       tc_fence_after();
       if (a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 5, (int)it);
       const int rbuf = has_res ? (int)(it % sp.res_bufs) : 0;
@@ -600,11 +635,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (a.tma_out && et == 0) tma_store_wait_all();
+    if (a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && et == 0) { a.trace[6 + team] = wepi; a.trace[12 + team] = clock64() - tstart_clk; }
   }
 
   // ---- teardown -----------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
+  if (a.trace != nullptr && a.trace_cap < 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0) a.trace[15] = clock64() - t_entry;
+    if (blockIdx.x < 32) a.trace[16 + blockIdx.x] = clock64() - t_entry;  // lifetime of the first CTAs
+    if (blockIdx.x >= gridDim.x - 8) a.trace[48 + blockIdx.x - (gridDim.x - 8)] = clock64() - t_entry;
+  }
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");

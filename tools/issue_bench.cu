@@ -28,6 +28,8 @@ struct TArgs {
   int warps;       // issuing warps
   int n_tiles;     // tiled: distinct tile rows / rows ; im2col: images
   int W;           // im2col: image width == height
+  int ctot;        // im2col: channels of the tensor (row_bytes of them per box); 0 = row_bytes
+  int walk;        // im2col: 1 = walk real 128-pixel tiles of the images (base pixel from the tile index)
   int noise;       // other warps of the CTA spin on an mbarrier meanwhile: 0 none, 1 try_wait loop with clock64
                    // checks (the library's mbar_wait), 2 try_wait loop with __nanosleep back-off
 };
@@ -70,6 +72,8 @@ __global__ void __launch_bounds__(640, 1) tma_issue_kernel(const __grid_constant
   int stage = 0;
   uint32_t phase = 0;
   int tap_r = 0, tap_s = 0, row0 = 0;
+  int cch = 0, bw = -1, bh = -1, bn = 0, wt = blockIdx.x * a.warps + w;  // walk state
+  (void)row0;
   long long issue_sum = 0;
   const long long t0 = clock64();
   for (int i = 0; i < a.iters; ++i) {
@@ -80,12 +84,26 @@ __global__ void __launch_bounds__(640, 1) tma_issue_kernel(const __grid_constant
       mbar_expect_tx(bar, box_bytes);
       const long long c0 = clock64();
       if (a.mode == 0) tma_load_2d(dst, &tm, bar, 0, tile * a.rows);
-      else tma_load_im2col_4d(dst, &tm, bar, 0, -1, row0 - 1, tile, (uint16_t)tap_s, (uint16_t)tap_r);
+      else tma_load_im2col_4d(dst, &tm, bar, cch, bw, bh, a.walk ? bn : tile, (uint16_t)tap_s, (uint16_t)tap_r);
       issue_sum += clock64() - c0;
     }
     __syncwarp();
     if (a.mode == 1) {  // the 9 taps of one tile, then another image
-      if (++tap_s == 3) { tap_s = 0; if (++tap_r == 3) { tap_r = 0; tile += tile_step; } }
+      if (a.ctot > a.row_bytes && cch + a.row_bytes < a.ctot) { cch += a.row_bytes; }
+      else {
+        cch = 0;
+        if (++tap_s == 3) { tap_s = 0; if (++tap_r == 3) {
+          tap_r = 0; tile += tile_step;
+          if (a.walk) {  // next 128-pixel tile: base pixel of output pixel m0 = wt * 128
+            wt += tile_step;
+            const int hw = a.W * a.W, tiles = 256 * hw / 128;
+            if (wt >= tiles) wt -= tiles;
+            const int m0 = wt * 128;
+            bn = m0 / hw; const int rem = m0 - bn * hw; const int p = rem / a.W;
+            bw = rem - p * a.W - 1; bh = p - 1;
+          }
+        } }
+      }
     } else {
       tile += tile_step;
     }
@@ -184,6 +202,72 @@ __global__ void __launch_bounds__(128, 1) umma_issue_kernel(MArgs a, long long *
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Interference: warps 0/1 issue tcgen05.mma (same or different accumulators) while warp 2 issues TMA boxes.
+struct CArgs { int n; int mma_warps; int same_acc; int tma_on; int iters; };
+
+__global__ void __launch_bounds__(128, 1) combo_kernel(const __grid_constant__ CUtensorMap tm, CArgs a, long long *cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ uint32_t tmem_slot;
+  __shared__ __align__(8) uint64_t bars[16];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 100 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
+  if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&bars[i]), 1); fence_barrier_init(); }
+  if (w == 3) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  long long t0 = clock64(), t1 = t0;
+  if (w < a.mma_warps) {
+    const uint32_t bar = smem_u32(&bars[w]);
+    const uint32_t idesc = (2u << 4) | ((uint32_t)(a.n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t dflags = make_smem_desc<128>(0);
+    const uint32_t acc = tmem + ((a.same_acc || w == 0) ? 0u : 256u);
+    uint32_t commits = 0;
+    for (int i = 0; i < a.iters; ++i) {
+      const uint32_t lo = ((base & 0x3FFFFu) >> 4) + (uint32_t)((i + w) % 2) * ((16384 + 36864) >> 4);
+      const uint64_t da = dflags | lo, db = dflags | (lo + (16384 >> 4));
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_i8(acc, da + 2 * k, db + 2 * k, idesc, 1);
+        if ((i & 3) == 3) umma_commit(bar);
+      }
+      __syncwarp();
+      if ((i & 3) == 3) { ++commits; if ((commits & 15) == 0) spin_wait(bar, (commits - 1) & 1); }
+    }
+    if (elect_one()) umma_commit(bar);
+    __syncwarp();
+    ++commits;
+    spin_wait(bar, (commits - 1) & 1);
+    t1 = clock64();
+    if (lane == 0) cycles[blockIdx.x * 4 + w] = t1 - t0;
+  } else if (w == 2 && a.tma_on) {
+    const uint32_t tb = base + 110 * 1024;
+    int stage = 0; uint32_t phase = 0; int tile = blockIdx.x;
+    for (int i = 0; i < a.iters; ++i) {
+      const uint32_t bar = smem_u32(&bars[4 + stage]);
+      if (i >= 4) spin_wait(bar, phase ^ 1);
+      if (elect_one()) { mbar_expect_tx(bar, 16384); tma_load_2d(tb + stage * 16384, &tm, bar, 0, tile * 128); }
+      __syncwarp();
+      tile += gridDim.x; if (tile >= 1536) tile -= 1536;
+      if (++stage == 4) { stage = 0; phase ^= 1; }
+    }
+    for (int s = 0; s < 4; ++s) { const int idx = a.iters - 1 - s; spin_wait(smem_u32(&bars[4 + (idx & 3)]), (uint32_t)((idx >> 2) & 1)); }
+    t1 = clock64();
+    if (lane == 0) cycles[blockIdx.x * 4 + 2] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (w == 3) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory"); }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -217,7 +301,7 @@ int main() {
   CK(cudaFuncSetAttribute(tma_issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   CK(cudaFuncSetAttribute(umma_issue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 
-  struct TC { int mode, rows, row_bytes, stages, warps; size_t bytes; int W; int noise = 0; };
+  struct TC { int mode, rows, row_bytes, stages, warps; size_t bytes; int W; int noise = 0; int ctot = 0; int walk = 0; };
   const TC tcs[] = {
       {0, 128, 128, 8, 1, 24u << 20, 0},  {0, 128, 128, 4, 1, 24u << 20, 0}, {0, 32, 128, 8, 1, 24u << 20, 0},
       {0, 256, 128, 4, 1, 24u << 20, 0},  {0, 128, 64, 8, 1, 24u << 20, 0},  {0, 128, 128, 4, 2, 24u << 20, 0},
@@ -228,11 +312,15 @@ int main() {
       {1, 128, 128, 4, 1, 0, 28, 1},      {1, 128, 128, 4, 1, 0, 28, 2},     {1, 128, 128, 4, 1, 0, 28, 3},
       {1, 128, 128, 4, 2, 0, 28, 1},      {1, 128, 128, 4, 2, 0, 28, 2},     {0, 128, 128, 4, 1, 24u << 20, 0, 1},
       {0, 128, 128, 4, 1, 24u << 20, 0, 2},
+      {1, 128, 128, 4, 1, 0, 14, 0, 256, 1}, {1, 128, 128, 4, 2, 0, 14, 0, 256, 1}, {1, 128, 128, 3, 4, 0, 14, 0, 256, 1},
+      {1, 128, 128, 4, 1, 0, 28, 0, 128, 1}, {1, 128, 128, 4, 2, 0, 28, 0, 128, 1},
+      {1, 128, 128, 4, 1, 0, 7, 0, 512, 1},  {1, 128, 128, 4, 2, 0, 7, 0, 512, 1},
+      {1, 128, 128, 4, 1, 0, 14, 0, 256, 0}, {1, 128, 128, 4, 2, 0, 14, 0, 256, 0},
   };
   for (const TC &c : tcs) {
     CUtensorMap tm;
     TArgs a{};
-    a.mode = c.mode; a.rows = c.rows; a.row_bytes = c.row_bytes; a.stages = c.stages; a.warps = c.warps; a.noise = c.noise;
+    a.mode = c.mode; a.rows = c.rows; a.row_bytes = c.row_bytes; a.stages = c.stages; a.warps = c.warps; a.noise = c.noise; a.ctot = c.ctot ? c.ctot : c.row_bytes; a.walk = c.walk;
     a.iters = 1800;
     const CUtensorMapSwizzle sw = c.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     CUresult r;
@@ -246,12 +334,12 @@ int main() {
                     sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       a.n_tiles = (int)(M / c.rows);
     } else {
-      const int W = c.W, C = c.row_bytes, N = 256;
+      const int W = c.W, C = c.ctot ? c.ctot : c.row_bytes, N = 256;
       cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)W, (cuuint64_t)N};
       cuuint64_t strides[3] = {(cuuint64_t)C, (cuuint64_t)W * C, (cuuint64_t)W * W * C};
       int lower[2] = {-1, -1}, upper[2] = {-1, -1};
       cuuint32_t es[4] = {1, 1, 1, 1};
-      r = enc_im2col(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, buf, dims, strides, lower, upper, (cuuint32_t)C,
+      r = enc_im2col(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, buf, dims, strides, lower, upper, (cuuint32_t)c.row_bytes,
                      (cuuint32_t)c.rows, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       a.n_tiles = N; a.W = W;
@@ -261,10 +349,37 @@ int main() {
     CK(cudaDeviceSynchronize());
     const double clk = avg148(cyc), icl = avg148(iss);
     printf("%s %3dB x%3d rows %s S=%d w%d noise=%d : %7.1f clk/box/warp  %6.1f B/clk/SM   issue instr %6.1f clk\n",
-           c.mode ? "im2col" : "tiled ", c.row_bytes, c.rows, c.mode ? (c.W == 28 ? "28x28" : "56x56") : (c.bytes > (64u << 20) ? "DRAM " : "L2   "),
+           c.mode ? "im2col" : "tiled ", c.row_bytes, c.rows, c.mode ? (c.W == 28 ? "28x28" : c.W == 56 ? "56x56" : c.W == 14 ? (c.walk ? "14x14 walk" : "14x14 fix ") : " 7x7  walk") : (c.bytes > (64u << 20) ? "DRAM " : "L2   "),
            c.stages, c.warps, c.noise, clk / a.iters, (double)a.iters * c.warps * c.rows * c.row_bytes / clk, icl / a.iters);
   }
 
+  if (getenv("COMBO")) {
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {128, (cuuint64_t)(24u << 20) / 128};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {128, 128};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, buf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { printf("encode failed\n"); return 1; }
+    CK(cudaFuncSetAttribute(combo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long *cyc4;
+    CK(cudaMalloc(&cyc4, 148 * 4 * sizeof(long long)));
+    for (int n : {144, 256}) for (int mw : {1, 2}) for (int same : {0, 1}) for (int tma : {0, 1}) {
+      if (mw == 1 && same == 1) continue;
+      CArgs a{n, mw, same, tma, 2000};
+      CK(cudaMemset(cyc4, 0, 148 * 4 * sizeof(long long)));
+      combo_kernel<<<148, 128, 200 * 1024>>>(tm, a, cyc4);
+      CK(cudaDeviceSynchronize());
+      long long h[148 * 4];
+      CK(cudaMemcpy(h, cyc4, sizeof(h), cudaMemcpyDeviceToHost));
+      double m0 = 0, m1 = 0, t2 = 0;
+      for (int i = 0; i < 148; ++i) { m0 += h[4 * i]; m1 += h[4 * i + 1]; t2 += h[4 * i + 2]; }
+      printf("combo N=%3d mma_warps=%d same_acc=%d tma=%d : warp0 %6.1f clk/MMA  warp1 %6.1f clk/MMA  tma %6.1f clk/box\n", n, mw, same, tma,
+             m0 / 148 / a.iters / 4, m1 / 148 / a.iters / 4, t2 / 148 / a.iters);
+    }
+    return 0;
+  }
   if (getenv("SKIP_UMMA")) return 0;
   const char *mname[] = {"SS i8 ", "SS f16", "TS i8 ", "cp    ", "cp+TS "};
   for (int mode = 0; mode < 5; ++mode) {
