@@ -138,13 +138,13 @@ constexpr int kTraceIssuers = 24;
 // trace_cap < 0 selects "wait statistics only": every role adds up the cycles it spends blocked in its
 // mbarrier waits and CTA 0 writes one total per role at the end (slot = role) -- no per-step overhead
 __device__ __forceinline__ void mbar_wait_stat(uint32_t bar, uint32_t parity, long long &sum, bool stats) {
-  if (!stats) { mbar_wait(bar, parity); return; }
+  if (!kDebugTrace || !stats) { mbar_wait(bar, parity); return; }
   const long long t0 = clock64();  // try_wait itself may suspend the thread: time the whole wait
   mbar_wait(bar, parity);
   sum += clock64() - t0;
 }
 __device__ __forceinline__ void trace_ev(const KernelArgs &a, int issuer, int &n, int ev, int idx) {
-  if (a.trace == nullptr || a.trace_cap < 0 || blockIdx.x != 0) return;
+  if (!kDebugTrace || a.trace == nullptr || a.trace_cap < 0 || blockIdx.x != 0) return;
   const int per = a.trace_cap / kTraceIssuers;
   if (n < per) {
     long long *p = a.trace + 3LL * (issuer * per + n);
@@ -342,8 +342,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int cur_i = -1, n_tile = 0, m0 = 0, cw = 0, chh = 0, cn = 0;
     int kb0 = 0, tap_r = 0, tap_s = 0, cchunk = 0;
     const int kb_step = step * grp;
-    const bool tracing = a.trace != nullptr && a.trace_cap >= 0;
-    const bool stats = a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0;
+    const bool tracing = kDebugTrace && a.trace != nullptr && a.trace_cap >= 0;
+    const bool stats = kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0;
     long long wsum = 0;
     const long long tstart_clk = clock64();
     const bool im2col = a.a_im2col != 0, streamed = !sp.b_resident;
@@ -444,8 +444,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t a_lo_first = desc_lo0 | ((smem_base & 0x3FFFFu) >> 4);
     const uint32_t b_lo_first = desc_lo0 | (((smem_base + (uint32_t)sp.b_off) & 0x3FFFFu) >> 4);
     const bool resident = sp.b_resident != 0;
-    const bool tracing = a.trace != nullptr && a.trace_cap >= 0;
-    const bool stats = a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0;
+    const bool tracing = kDebugTrace && a.trace != nullptr && a.trace_cap >= 0;
+    const bool stats = kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0;
     long long wfull = 0, wacc = 0;
     const long long tstart_clk = clock64();
     const int items = walk.count * ngrp;
@@ -544,9 +544,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         last_n_tile = n_tile;
         named_bar_sync(1 + team, kTeam);
       }
-      mbar_wait_stat(tfull_bar(tb), ph, wepi, a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0);
+      mbar_wait_stat(tfull_bar(tb), ph, wepi, kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0);
       tc_fence_after();
-      if (a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 5, (int)it);
+      if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 5, (int)it);
       const int rbuf = has_res ? (int)(it % sp.res_bufs) : 0;
       const uint32_t rsb = smem_base + sp.res_off + rbuf * kOutTileBytes;
       if (has_res) mbar_wait(rfull_bar(rbuf), (uint32_t)((it / sp.res_bufs) & 1));
@@ -622,7 +622,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      if (a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
+      if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
       mbar_arrive(tempty_bar(tb));  // kTeam arrivals release the accumulator buffer
       if (has_res) mbar_arrive(rempty_bar(rbuf));
       if (a.tma_out) {
@@ -635,13 +635,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (a.tma_out && et == 0) tma_store_wait_all();
-    if (a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && et == 0) { a.trace[6 + team] = wepi; a.trace[12 + team] = clock64() - tstart_clk; }
+    if (kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && et == 0) { a.trace[6 + team] = wepi; a.trace[12 + team] = clock64() - tstart_clk; }
   }
 
   // ---- teardown -----------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (a.trace != nullptr && a.trace_cap < 0 && threadIdx.x == 0) {
+  if (kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && threadIdx.x == 0) {
     if (blockIdx.x == 0) a.trace[15] = clock64() - t_entry;
     if (blockIdx.x < 32) a.trace[16 + blockIdx.x] = clock64() - t_entry;  // lifetime of the first CTAs
     if (blockIdx.x >= gridDim.x - 8) a.trace[48 + blockIdx.x - (gridDim.x - 8)] = clock64() - t_entry;
@@ -887,6 +887,10 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
 extern "C" void slq_conv_destroy(slq_conv *c) { delete c; }
 
 extern "C" int slq_debug_set_trace(int64_t *buf, int32_t capacity_events) {
+  if (!kDebugTrace && buf != nullptr) {
+    set_error("slq_debug_set_trace: this library was built without SLQ_DEBUG_TRACE (python slq_build.py --debug)");
+    return SLQ_ERR_UNSUPPORTED;
+  }
   g_trace = reinterpret_cast<long long *>(buf);
   g_trace_cap = buf ? capacity_events : 0;
   return SLQ_OK;

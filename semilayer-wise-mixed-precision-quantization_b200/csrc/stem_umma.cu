@@ -89,8 +89,9 @@ struct StemArgs {
   int dbg;  // $SLQ_STEM_DBG bit mask (timing experiments only): 1 skip A build, 2 skip pooling, 4 skip epilogue math
 };
 
+#define SF_DBG(a) (kDebugTrace ? (a).dbg : 0)
 __device__ __forceinline__ void stem_trace(const StemArgs &a, int issuer, int &n, int ev, int idx) {
-  if (a.trace == nullptr || blockIdx.x != 0) return;
+  if (!kDebugTrace || a.trace == nullptr || blockIdx.x != 0) return;
   const int per = a.trace_cap / 24;
   if (n < per) {
     long long *p = a.trace + 3LL * (issuer * per + n);
@@ -262,22 +263,22 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
       for (int p = p0; p < p1; ++p, ++rc) {
         const int ab = rc & 1;
         if (t == 0) stem_trace(a, 0, tn, 0, rc);
-        if (p + 1 < p1 && !(a.dbg & 16)) load_rows(2 * p + 4, 2 * p + 6, nxt, false);  // in flight during the build
+        if (p + 1 < p1 && !(SF_DBG(a) & 16)) load_rows(2 * p + 4, 2 * p + 6, nxt, false);  // in flight during the build
         mbar_wait(aempty_bar(ab), (uint32_t)(((rc >> 1) & 1) ^ 1));
         if (t == 0) stem_trace(a, 0, tn, 1, rc);
         uint8_t *atile = smem + kSfAOff + ab * kSfABytes;
-        if (!(a.dbg & 1)) {
+        if (!(SF_DBG(a) & 1)) {
           if (part == 0) stem_build_chunks<0, 6>(ring + 2 * q, atile + q * 128, q & 7, p);
           else if (part == 1) stem_build_chunks<6, 11>(ring + 2 * q, atile + q * 128, q & 7, p);
           else if (part == 2) stem_build_chunks<11, 16>(ring + 2 * q, atile + q * 128, q & 7, p);
           else stem_build_chunks<16, 21>(ring + 2 * q, atile + q * 128, q & 7, p);
         }
         if (t == 0) stem_trace(a, 0, tn, 2, rc);
-        if (!(a.dbg & 8)) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        if (!(SF_DBG(a) & 8)) fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         mbar_arrive(afull_bar(ab));
         if (t == 0) stem_trace(a, 0, tn, 3, rc);
         if (p + 1 < p1) {
-          if (!(a.dbg & 16)) store_rows(2 * p + 4, 2 * p + 6, nxt);
+          if (!(SF_DBG(a) & 16)) store_rows(2 * p + 4, 2 * p + 6, nxt);
           named_bar_sync(1, kSfBuilders);  // the next row's inputs are complete
         }
         if (t == 0) stem_trace(a, 0, tn, 8, rc);
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(tempty_bar(ab));  // accumulator is in registers: the next row may start
-        if (a.dbg & 4) continue;
+        if (SF_DBG(a) & 4) continue;
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
         named_bar_sync(2, kSfEpi);  // conv row p is complete in the ring
         if (et == 0) stem_trace(a, 18, tn, 11, rc);
         // pooled row j = max over conv rows 2j-1..2j+1: complete after an odd row or the last row
-        if (!((p & 1) || p == a.Hc - 1) || (a.dbg & 2)) continue;
+        if (!((p & 1) || p == a.Hc - 1) || (SF_DBG(a) & 2)) continue;
         const int j = p >> 1;
         if (j < j0) continue;  // the seam row only feeds this unit's first pooled row
         // one thread per (pooled column, 16 channels): 9 clamped 16-byte loads (a duplicated row or

@@ -8,6 +8,14 @@
 
 namespace slq {
 
+// Timeline tracing / wait statistics (slq_debug_set_trace, $SLQ_STEM_DBG) exist only in the debug build of
+// the library (-DSLQ_DEBUG_TRACE=1, `python slq_build.py --debug` -> libslq_b200_dbg.so): the control loops
+// of the kernels run at several cycles per dependent instruction, so even a never-taken branch per step costs.
+#ifndef SLQ_DEBUG_TRACE
+#define SLQ_DEBUG_TRACE 0
+#endif
+constexpr bool kDebugTrace = SLQ_DEBUG_TRACE != 0;
+
 // ------------------------------------------------------------------------------------------
 // PTX wrappers
 // ------------------------------------------------------------------------------------------

@@ -39,8 +39,12 @@ def needs_build():
     return open(STAMP).read().strip() != _digest()
 
 
-def build(force=False, verbose=False):
-    """Builds libslq_b200.so if the sources changed.  Returns the library path."""
+def build(force=False, verbose=False, debug=False):
+    """Builds libslq_b200.so if the sources changed.  Returns the library path.
+    debug=True builds libslq_b200_dbg.so instead: the same kernels with the timeline tracer / wait
+    statistics compiled in (-DSLQ_DEBUG_TRACE=1), used by tools/trace_*.py and tools/wait_stats.py."""
+    if debug:
+        return _build_debug(verbose)
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -66,5 +70,33 @@ def build(force=False, verbose=False):
     return LIB
 
 
+LIB_DBG = os.path.join(HERE, "libslq_b200_dbg.so")
+
+
+def _build_debug(verbose=False):
+    stamp = os.path.join(HERE, "build", "dbg", "sources.sha256")
+    if os.path.exists(LIB_DBG) and os.path.exists(stamp) and open(stamp).read().strip() == _digest():
+        return LIB_DBG
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    os.makedirs(os.path.join(HERE, "build", "dbg"), exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(HERE, "build", "dbg", src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-DSLQ_DEBUG_TRACE=1", "-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out.decode())
+            raise RuntimeError("nvcc failed on %s" % src)
+    subprocess.check_call([nvcc, "-shared", "-o", LIB_DBG] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    with open(stamp, "w") as f:
+        f.write(_digest())
+    return LIB_DBG
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))

@@ -71,9 +71,13 @@ class SlqError(RuntimeError):
 
 
 def lib():
-    """Loads libslq_b200.so (building is __graft_entry__.build()'s / slq_build.build()'s job)."""
-    global _lib
+    """Loads libslq_b200.so (building is __graft_entry__.build()'s / slq_build.build()'s job).
+    $SLQ_DEBUG_LIB=1 loads the tracing build libslq_b200_dbg.so instead (developer tools only)."""
+    global _lib, LIB_PATH
     if _lib is None:
+        if os.environ.get("SLQ_DEBUG_LIB") == "1":
+            import slq_build
+            LIB_PATH = slq_build.build(debug=True)
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 "libslq_b200.so is missing (%s). Build it with `python slq_build.py`; this package "

@@ -11,6 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "semilayer-wise-mixed-precision-quantization_b200"))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
+os.environ.setdefault("SLQ_DEBUG_LIB", "1")  # the tracing build of the library
 import slq_lib as L  # noqa: E402
 from helpers import ConvCase  # noqa: E402
 

@@ -4,6 +4,7 @@ import numpy as np
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "semilayer-wise-mixed-precision-quantization_b200"))
+os.environ.setdefault("SLQ_DEBUG_LIB", "1")  # the tracing build of the library
 import slq_lib as L
 lib = L.lib()
 N, H, W = 256, 224, 224
