@@ -126,7 +126,8 @@ struct KernelArgs {
   int num_grp;         // pipeline steps per tile = num_kb / sp.group
   int chunks_per_tap;  // Cin / SWZ
   int tma_out;         // 1: u8/s8 output through the smem tile + TMA store
-  int mma_warps_per_tile;  // MMA warps that touch one tile: 2, or 1 when a tile is a single K block
+  int mma_warps_per_tile;  // MMA warps that touch one tile: 2, or 1 when a tile is a single K block / tile_alt
+  int tile_alt;            // the two MMA warps alternate whole tiles instead of pipeline steps
   long long m_tiles;
   long long *trace;    // debug: CTA 0 logs (event, index, clock) triples here (slq_debug_set_trace)
   int trace_cap;
@@ -454,11 +455,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(bfull_bar, 0);  // the CTA's weights are in shared memory
       tc_fence_after();
     }
-    int i = w / ngrp, gi = w - i * ngrp;  // w < 2
-    int stage = w % n_stages;
-    uint32_t phase = (uint32_t)((w / n_stages) & 1);
+    // Which steps this warp issues.  Default: alternate steps (c = w, w + 2, ...), both warps feed the same
+    // tile.  tile_alt: alternate whole TILES (tile i -> warp i & 1), so short tiles (2-3 steps) do not make
+    // the second warp idle through the first step waiting for tstart; the host enables it when the pipeline
+    // depth is a multiple of 2 * steps-per-tile (each stage barrier then always has the same waiter).
+    const bool tile_alt = a.tile_alt != 0;
+    int i = tile_alt ? w : w / ngrp, gi = tile_alt ? 0 : w - i * ngrp;  // w < 2
+    int c0 = tile_alt ? w * ngrp : w;
+    int stage = c0 % n_stages;
+    uint32_t phase = (uint32_t)((c0 / n_stages) & 1);
     int cur_i = -1, acc = 0, tb = 0;
-    for (int c = w; c < items; c += nmw) {
+    for (int c = c0; c < items;) {
       if (i != cur_i) {  // this warp's first step of tile i
         cur_i = i;
         acc = i % kAccBufs;
@@ -473,7 +480,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t tmem_d = tmem_u + acc * kAccStride;
       const uint32_t a_lo = a_lo_first + (uint32_t)stage * stage16;
       const uint32_t b_lo = resident ? b_lo_first + (uint32_t)(gi * grp) * btile16 : a_lo + a16;
-      const bool last_mine = gi + nmw >= ngrp;  // this warp's last step of the tile
+      const bool last_mine = tile_alt ? gi + 1 == ngrp : gi + nmw >= ngrp;  // this warp's last step of the tile
       if (tracing && lane == 0) trace_ev(a, 16 + 3 * w, tn, 7, c);
       mbar_wait_stat(full_bar(stage), phase, wfull, stats);
       tc_fence_after();
@@ -490,10 +497,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (last_mine) umma_commit(tfull_bar(tb));  // this warp's share of the accumulator is complete
       }
       __syncwarp();
-      gi += nmw;
-      while (gi >= ngrp) { gi -= ngrp; ++i; }
-      stage += nmw;
-      if (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
+      if (tile_alt) {
+        int adv = 1;
+        if (++gi == ngrp) { gi = 0; i += 2; adv += ngrp; }  // skip the other warp's tile
+        c += adv; stage += adv;
+        while (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
+      } else {
+        c += nmw;
+        gi += nmw;
+        while (gi >= ngrp) { gi -= ngrp; ++i; }
+        stage += nmw;
+        if (stage >= n_stages) { stage -= n_stages; phase ^= 1; }
+      }
     }
     if (stats && lane == 0) { a.trace[2 + w] = wfull; a.trace[4 + w] = wacc; a.trace[10 + w] = clock64() - tstart_clk; }
   } else if (warp >= 4) {
@@ -790,7 +805,9 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   a.chunks_per_tap = c->g.Cin / SWZ;
   a.num_kb = c->g.kh * c->g.kw * a.chunks_per_tap;
   a.num_grp = a.num_kb / a.sp.group;
-  a.mma_warps_per_tile = (a.sp.mma_warps == 2 && a.num_grp >= 2) ? 2 : 1;
+  static const bool no_tile_alt = getenv("SLQ_NO_TILE_ALT") != nullptr;  // experiments only
+  a.tile_alt = (!no_tile_alt && a.sp.mma_warps == 2 && a.num_grp >= 2 && a.sp.stages % (2 * a.num_grp) == 0) ? 1 : 0;
+  a.mma_warps_per_tile = (a.sp.mma_warps == 2 && a.num_grp >= 2 && !a.tile_alt) ? 2 : 1;
   a.m_tiles = ceil_div(c->g.M, kTileM);
   a.tma_out = tma_out;
   // Programmatic dependent launch: this grid's CTAs may start (barrier / TMEM set-up, resident weights)
