@@ -129,7 +129,14 @@ def run_reference(args):
     if rank != 0:
         return
     batch = args.ref_batch
-    times, threads = cpu_reference_forward(args.arch, batch, args.steps + args.warmup)
+    # all the host threads this process may use: torchrun pins OMP_NUM_THREADS=1 per rank, and only rank 0
+    # runs this arm, so take the cores of its affinity mask instead
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = str(threads)  # before torch is imported
+    times, threads = cpu_reference_forward(args.arch, batch, args.steps + args.warmup, threads=threads)
     times = times[args.warmup:] if len(times) > args.warmup else times
     total = sum(times)
     val = batch * len(times) / total
@@ -420,11 +427,11 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            times, threads = cpu_reference_forward(args.arch, 16, 3)
-            v = 16 / min(times)
+            times, threads = cpu_reference_forward(args.arch, 32, 16)
+            v = 32 * len(times) / sum(times)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "best of 3 fp32 forwards of batch 16 on the host CPU "
-                                              "(stock torch ops = the reference's own arithmetic)"}
+                                    "sample": "%d fp32 forwards of batch 32 (%.1f s) on the host CPU after one warm-up "
+                                              "(stock torch ops = the reference's own arithmetic)" % (len(times), sum(times))}
         except Exception as e:
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": "failed: %s" % e}
