@@ -55,6 +55,7 @@ struct SmemPlan {
   int mma_warps;     // 2: warps 1 and 3 issue MMAs (1: warp 1 only; experiments)
   int b_off;
   int res_bufs;      // depth of the residual (block identity) prefetch ring, 0 without residual
+  int out_bufs;      // output staging tiles: one per epilogue team, or ONE shared by both (streamed weights)
   int out_off, res_off, prm_off, bar_off;
   int total;         // dynamic smem bytes to request (including 1024 B of alignment slack)
 };
@@ -82,15 +83,19 @@ inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
       if (num_kb % grp != 0 || (force_group && grp > force_group)) continue;
       const int st = (int)std::min<long long>(kMaxStages, room / ((long long)grp * p.a_bytes)) & ~1;
       if (st >= (grp == 1 ? 4 : 4)) {
-        p.b_resident = 1; p.group = grp; p.stages = st; p.stage_bytes = grp * p.a_bytes; p.res_bufs = rb;
+        p.b_resident = 1; p.group = grp; p.stages = st; p.stage_bytes = grp * p.a_bytes; p.res_bufs = rb; p.out_bufs = 2;
         break;
       }
     }
     if (!has_res) break;
   }
   if (p.stages == 0) {
+    // streamed weights: these are the K-heavy layers -- few tiles per CTA, epilogue teams idle 80 % of the
+    // time, and the {A, B} ring is what runs short (2 -> 4 stages: 54 -> 37 us on the 3x3 256 layer), so
+    // the two teams share ONE staging tile and the 16 KB go to the ring (6 stages without residual)
     p.res_bufs = has_res ? kMaxResBufs : 0;
-    const int fixed = (2 + p.res_bufs) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
+    p.out_bufs = 1;
+    const int fixed = (p.out_bufs + p.res_bufs) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
     p.b_resident = 0;
     p.group = 1;
     p.stage_bytes = p.a_bytes + p.b_tile_bytes;
@@ -99,7 +104,7 @@ inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
   p.mma_warps = force_mma ? force_mma : 2;
   p.b_off = p.stages * p.stage_bytes;
   p.out_off = p.b_off + (p.b_resident ? (int)b_all : 0);
-  p.res_off = p.out_off + 2 * kOutTileBytes;
+  p.res_off = p.out_off + p.out_bufs * kOutTileBytes;
   p.prm_off = p.res_off + p.res_bufs * kOutTileBytes;
   p.bar_off = p.prm_off + 2 * 128 * 16;
   p.total = 1024 + p.bar_off + 512;
@@ -227,6 +232,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto rfull_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + b); };
   auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + kMaxResBufs + b); };
   const uint32_t bfull_bar = bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs);  // resident B landed
+  auto stfree_bar = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs + 2 + t); };
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(
       smem + sp.bar_off + 8 * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs + 1));
 
@@ -265,6 +271,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(rempty_bar(b), kTeam);
     }
     mbar_init(bfull_bar, 1);
+    mbar_init(stfree_bar(0), 1);
+    mbar_init(stfree_bar(1), 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -527,7 +535,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // fetches the same constant of FOUR channels: 3 wavefronts per channel instead of 4, 0.75 loads per output.
     float *prm = reinterpret_cast<float *>(smem + sp.prm_off) + team * 512;
     const uint32_t prm_s = smem_base + sp.prm_off + team * 128 * 16;
-    const uint32_t stg = smem_base + sp.out_off + team * kOutTileBytes;
+    const bool shared_stg = sp.out_bufs == 1;  // both teams stage through one tile (stfree hand-off below)
+    const uint32_t stg = smem_base + sp.out_off + (shared_stg ? 0 : team) * kOutTileBytes;
     float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
     if (OUT != SLQ_OUT_ACC) {
       s_in = e.act_scales[e.in_id];
@@ -630,6 +639,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (kQuant) {
+          // shared staging tile: the other team's store of the previous tile must have read it
+          if (shared_stg && u == u0 && it >= 1) mbar_wait(stfree_bar(team ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
 #pragma unroll
           for (int i = 0; i < CW / 16; ++i)
             sts128(stg + stage_off(row, u * (CW / 16) + i, g.bn_ch),
@@ -646,6 +657,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (et == 0) {
           tma_store_2d(&tmO, stg, n_tile * g.bn_ch, (int)(m_tile * kTileM));  // rows >= M are clipped
           tma_store_commit();
+          if (shared_stg) {  // hand the tile to the other team as soon as the TMA engine has read it
+            tma_store_wait_read();
+            mbar_arrive(stfree_bar(team));
+          }
         }
       }
     }
