@@ -11,9 +11,11 @@
 //   S[m] = sum_k A[m, k] that the zero-point correction z[oc]*S[m] needs.
 //
 // Persistent, warp-specialised CTA (640 threads, 1 CTA/SM):
-//   warp 0      TMA producer (A, resident B, residual tiles); smem ring of kStages x {A 128xSWZ [, B (bn+16)xSWZ]}
-//   warp 1, 3   tcgen05.mma issuers: K blocks alternate between the two; accumulator ring of 3 in TMEM
-//   warp 2      TMEM allocator, then second A producer (resident weights) or B producer (streamed weights)
+//   warps 0, 2  TMA producers: pipeline step c (one smem stage = 1-4 K blocks of A, plus the K block's B tile
+//               when the weights are streamed) belongs to producer c & 1; warp 0 also loads the resident
+//               weights once and one residual tile per output tile; warp 2 allocates TMEM first
+//   warps 1, 3  tcgen05.mma issuers: steps (or, on short tiles, whole tiles) alternate between the two;
+//               accumulator ring of 3 in TMEM
 //   warps 4-11  epilogue team 0  \  tile i -> team i&1, accumulator buffer i%3.  A team is 8 warps:
 //   warps 12-19 epilogue team 1  /  two per TMEM lane quarter, each taking half of the tile's channels:
 //               tcgen05.ld -> dequant + folded BN + residual + ReLU -> u8 into a swizzled smem tile
@@ -316,9 +318,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   //   residual tiles    : warp 0, one box per tile, up to a tile ahead of the A tiles it is loading
   //   resident weights  : land once, issued by warp 0
   const int w_mma1 = sp.mma_warps == 2 ? 3 : -1;  // second MMA warp
-  const int n_a_warps = 2;
   const int a_idx = warp == 0 ? 0 : (warp == 2 ? 1 : -1);
-  constexpr bool b_warp = false;
   if (a_idx >= 0) {
     const uint32_t b_bytes = (uint32_t)(bn_cols * SWZ);
     const int grp = sp.group;
