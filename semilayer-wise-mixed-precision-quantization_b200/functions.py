@@ -49,6 +49,14 @@ class PackedRows:
         return raw[:self.K].astype(np.int32)
 
 
+def packed_row_bytes(K, bits):
+    """slq_packed_row_bytes (include/slq.h) for an array of bit-widths <= 8 at once -- a ctypes call per
+    row would dominate a whole-model pass: 4-bit rows pack two codes per byte, 2-bit rows four, every other
+    width one."""
+    b64 = np.asarray(bits, dtype=np.int64)
+    return np.where(b64 == 4, (K + 1) // 2, np.where(b64 == 2, (K + 3) // 4, K)).astype(np.int64)
+
+
 def _div_mode_for(tensor, div_mode):
     if div_mode is not None:
         return div_mode
@@ -75,11 +83,7 @@ def quantize_rows(tensor, rows, bits, write_back=True, want_codes=True, div_mode
     if bits_h.size and (bits_h.min() < 1 or bits_h.max() > 8):
         raise ValueError("bit-width must be in 1..8")
     n_jobs = rows_h.size
-    # slq_packed_row_bytes for every job at once (a ctypes call per row would dominate a whole-model pass):
-    # 4-bit rows pack two codes per byte, 2-bit rows four, everything else up to 8 bits one
-    b64 = bits_h.astype(np.int64)
-    sizes = np.where(b64 == 4, (K + 1) // 2, np.where(b64 == 2, (K + 3) // 4, K))
-    sizes = (sizes + 15) // 16 * 16
+    sizes = (packed_row_bytes(K, bits_h) + 15) // 16 * 16
     offs_h = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64) if n_jobs else np.zeros(0, np.int64)
     total = int(sizes.sum())
     dm = _div_mode_for(tensor, div_mode)

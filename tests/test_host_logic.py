@@ -127,3 +127,31 @@ def test_engine_invalidation_hooks(monkeypatch):
     net._slq_dirty = False
     net.to("cpu")
     assert net._slq_dirty
+
+
+def test_loader_side_formats():
+    """imagenet.py mirror: raw u8 batches and the CPU normalisation the stem kernel reproduces
+    (reference imagenet.py:14-15: ToTensor then Normalize(mean, std))."""
+    import imagenet
+    (x8, y), = imagenet.synthetic_loader(1, 3, 16, seed=5, dtype=torch.uint8)
+    assert x8.dtype == torch.uint8 and x8.shape == (3, 3, 16, 16) and y.dtype == torch.int64
+    got = imagenet.normalize_u8(x8)
+    mean = torch.tensor(imagenet.MEAN).view(1, 3, 1, 1)
+    std = torch.tensor(imagenet.STD).view(1, 3, 1, 1)
+    want = (x8.float() / 255 - mean) / std
+    assert got.dtype == torch.float32 and torch.equal(got, want)
+    (xh, _), = imagenet.synthetic_loader(1, 2, 8, seed=5, dtype=torch.float16)
+    (xf, _), = imagenet.synthetic_loader(1, 2, 8, seed=5)
+    assert xh.dtype == torch.float16 and torch.equal(xh, xf.half())
+
+
+def test_packed_row_sizes_match_the_library():
+    """functions.quantize_rows sizes the packed-code blob with vectorised arithmetic; it must agree with
+    slq_packed_row_bytes (a pure host function of the library) for every bit-width and row length."""
+    import functions
+    import slq_lib as L
+    lib = L.lib()
+    bits = np.arange(1, 9)
+    for K in (1, 3, 64, 65, 576, 1152, 4608):
+        want = [lib.slq_packed_row_bytes(K, int(b)) for b in bits]
+        assert functions.packed_row_bytes(K, bits).tolist() == want, K
