@@ -60,6 +60,9 @@ def packed_row_bytes(K, bits):
 def _div_mode_for(tensor, div_mode):
     if div_mode is not None:
         return div_mode
+    forced = os.environ.get("SLQ_DIV_MODE")  # "true" | "recip": pin one flavour for a whole run (tests)
+    if forced:
+        return {"true": L.DIV_TRUE, "recip": L.DIV_RECIP}[forced]
     # what the reference's own ATen call does on that device
     return L.DIV_RECIP if tensor.is_cuda else L.DIV_TRUE
 
@@ -118,7 +121,7 @@ def quantize_rows(tensor, rows, bits, write_back=True, want_codes=True, div_mode
             L.check(rc)
         st_h = status
     if write_back:
-        resnet.bump_weight_epoch()
+        resnet.note_weight_write(tensor)  # engines re-pack exactly this tensor's layer on their next forward
     if bool((st_h & L.ROW_ZERO_RANGE).any()):
         raise ZeroDivisionError("float division by zero")
     return PackedRows(rows_h, bits_h, offs_h, blob, z, s32, status, K)
@@ -138,7 +141,7 @@ def channel_wise_quantizationperchan(tensor, bit, i):
         quantize_rows(tensor, [i], [bit], write_back=True, want_codes=False)
     else:
         tensor[i] = quantize_wgt(tensor[i], bit)
-        resnet.bump_weight_epoch()
+        resnet.note_weight_write(tensor)
     return tensor
 
 

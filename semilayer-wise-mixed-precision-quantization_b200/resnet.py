@@ -30,13 +30,28 @@ model_urls = {
     "resnet50": "https://download.pytorch.org/models/resnet50-19c8e357.pth",
 }
 
-# bumped by functions.channel_wise_quantizationperchan & co.: any engine compiled before the bump
-# re-derives its packed weights from the (mutated) fp32 tensors on its next forward
+# ---- how the compiled engines learn that a weight tensor was written ---------------------
+# The mains mutate ``conv.weight.data`` in place through functions.channel_wise_quantizationperchan; a write
+# through ``.data`` does not bump the Parameter's ``_version``.  Every quantizer entry point therefore notes
+# the STORAGE it wrote (note_weight_write); an engine compares, per layer, (storage pointer, ``_version``,
+# write count) with what it packed last and re-derives only the layers that differ.  ``load_state_dict``
+# bumps ``_version`` and ``.to()`` / ``.data = ...`` change the pointer, so those are seen without a hook.
+# WEIGHT_EPOCH is the conservative fallback for writers that cannot name a tensor (re-checks every layer).
 WEIGHT_EPOCH = [0]
+_WRITES = {}
 
 
 def bump_weight_epoch():
     WEIGHT_EPOCH[0] += 1
+
+
+def note_weight_write(tensor):
+    key = tensor.untyped_storage().data_ptr()
+    _WRITES[key] = _WRITES.get(key, 0) + 1
+
+
+def weight_write_count(tensor):
+    return _WRITES.get(tensor.untyped_storage().data_ptr(), 0)
 
 
 def _conv(cin, cout, k, stride=1):
@@ -121,25 +136,33 @@ class ResNet(nn.Module):
         seq += [block(self.inplanes, planes) for _ in range(1, blocks)]
         return nn.Sequential(*seq)
 
-    # ---- anything that can change parameters invalidates the compiled engines ----------------
+    # ---- compiled-engine bookkeeping ---------------------------------------------------------
     def slq_invalidate(self):
+        """Forces every layer to be re-packed on the next forward (for writers the engine cannot see,
+        e.g. ``w.data.mul_(2)``: an in-place op through ``.data`` bumps no version counter)."""
         self._slq_dirty = True
 
     def _apply(self, fn, *a, **k):  # .to() / .cuda() / .float() ...
-        before = self.conv1.weight.data_ptr()
+        before = (self.conv1.weight.data_ptr(), self.conv1.weight.dtype)
         out = super()._apply(fn, *a, **k)
-        self._slq_dirty = True
-        if self.conv1.weight.data_ptr() != before:  # storage moved: compiled pointers are stale
+        if (self.conv1.weight.data_ptr(), self.conv1.weight.dtype) != before:
+            # storage moved or was converted: compiled pointers are stale.  A no-op ``net.to(device)``
+            # (evaluate_acc_loss_softmax calls it before every evaluation, functions.py:97) keeps the
+            # engine, its packed weights, its activation scales and its CUDA graphs.
             self._slq_engines = {}
+            self._slq_dirty = True
         return out
 
-    def load_state_dict(self, *a, **k):
-        self._slq_dirty = True
-        return super().load_state_dict(*a, **k)
+    def __getstate__(self):  # copy.deepcopy / torch.save(net): engines own ctypes handles and GBs of HBM
+        state = dict(self.__dict__)
+        state["_slq_engines"] = {}
+        state["_slq_dirty"] = True
+        return state
 
-    def train(self, mode=True):
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        self.__dict__.setdefault("_slq_engines", {})
         self._slq_dirty = True
-        return super().train(mode)
 
     def slq_engine(self, x, **kw):
         """The compiled engine for inputs shaped like x (built on first use)."""
@@ -147,10 +170,39 @@ class ResNet(nn.Module):
         key = (x.shape[0], x.shape[2], x.shape[3], x.device.index)
         eng = self._slq_engines.get(key)
         if eng is None:
+            old = next(iter(self._slq_engines.values()), None)
             eng = slq_engine.Engine(self, x.shape[0], x.shape[2], x.shape[3], x.device, **kw)
+            if old is not None and old.calibrated and len(old.act) == len(eng.act) and old.calib_hw == (x.shape[2], x.shape[3]):
+                eng.adopt_scales(old)  # same network, same image size, other batch size: ranges carry over
             self._slq_engines = {key: eng}  # one live shape at a time (activation buffers are large)
-            self._slq_dirty = True
         return eng
+
+    def slq_calibrate(self, batches, headroom=1.0):
+        """Explicit calibration of the static per-tensor activation scales (the reference never quantises
+        activations, SURVEY.md F2, so this call has no counterpart there): running abs-max over ``batches``
+        (a tensor, a list of tensors, or a loader of (x, y) pairs; CUDA or host), times ``headroom``.
+        The scales then stay fixed -- through weight changes, state_dict reloads and later batches -- until
+        the next slq_calibrate().  Without this call the first forward calibrates on its own batch."""
+        import slq_engine
+        if torch.is_tensor(batches):
+            batches = [batches]
+        dev = self.conv1.weight.device
+        first = True
+        for item in batches:
+            x = item[0] if isinstance(item, (tuple, list)) else item
+            x = x.to(dev, non_blocking=True)
+            cap = slq_engine.engine_batch(self, x.shape[0])
+            if x.shape[0] < cap:
+                xp = x.new_zeros((cap,) + tuple(x.shape[1:]))
+                xp[:x.shape[0]] = x
+                x = xp
+            eng = self.slq_engine(x)
+            eng.sync_weights(force=self._slq_dirty)
+            self._slq_dirty = False
+            eng.calibrate(x, accumulate=not first, headroom=headroom)
+            first = False
+        if first:
+            raise ValueError("slq_calibrate: no batches")
 
     def forward(self, x):
         if not x.is_cuda:
@@ -169,11 +221,10 @@ class ResNet(nn.Module):
         else:
             xp = x
         eng = self.slq_engine(xp)
-        if self._slq_dirty or eng.epoch != WEIGHT_EPOCH[0]:
-            eng.refresh_weights()
+        eng.sync_weights(force=self._slq_dirty)  # re-packs only the layers whose tensors were written
+        self._slq_dirty = False
+        if not eng.calibrated:
             eng.calibrate(xp)
-            eng.epoch = WEIGHT_EPOCH[0]
-            self._slq_dirty = False
         return eng.forward(xp)[:n].clone()
 
 

@@ -109,16 +109,18 @@ class Engine:
     @classmethod
     def for_module(cls, net, x, **kw):
         """Engine for ANY module tree shaped like the reference's ResNet (resnet.py:121-202), e.g. the
-        reference's own class patched per INTEGRATION.md B.2: cached on the module, re-packed and
-        re-calibrated on first use (call ``net._slq_engine = None`` after mutating weights)."""
+        reference's own class patched per INTEGRATION.md B.2: cached on the module, layers whose
+        tensors were written are re-packed on every call; calibrated on first use."""
         key = (tuple(x.shape), x.device.index)
         cached = getattr(net, "_slq_engine", None)
         if cached is None or cached[0] != key:
             eng = cls(net, x.shape[0], x.shape[2], x.shape[3], x.device, **kw)
-            eng.refresh_weights()
-            eng.calibrate(x)
             net._slq_engine = cached = (key, eng)
-        return cached[1]
+        eng = cached[1]
+        eng.sync_weights()
+        if not eng.calibrated:
+            eng.calibrate(x)
+        return eng
 
     # ------------------------------------------------------------------------------------------
     def _new_act(self, shape_nhwc, signed=False):
@@ -172,8 +174,21 @@ class Engine:
         self.absmax_tmp = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pooled = torch.empty((N, self.final_c), dtype=torch.float32, device=dev)
         self.logits = torch.empty((N, net.fc.out_features), dtype=torch.float32, device=dev)
+        self.stem_w = torch.zeros_like(net.conv1.weight, dtype=torch.float32, device=dev)
+        self.stem_a = torch.zeros(64, dtype=torch.float32, device=dev)
+        self.stem_b = torch.zeros(64, dtype=torch.float32, device=dev)
+        self.fc_w = torch.zeros_like(net.fc.weight, dtype=torch.float32, device=dev)
+        self.fc_b = torch.zeros_like(net.fc.bias, dtype=torch.float32, device=dev)
+        self.ends_sig = None
+        self.weights_version = 0   # bumped by every sync_weights() that changed something
         self.calibrated = False
+        self.calib_hw = (self.H, self.W)
         self._graphs, self._seen = {}, set()
+
+    def adopt_scales(self, other):
+        """Takes over the activation scales of another engine of the same network (other batch size)."""
+        self.act_scales.copy_(other.act_scales)
+        self.calibrated = True
 
     def _make_op(self, conv, bn, in_id, h, w, relu, signed=False):
         op = _ConvOp()
@@ -187,48 +202,106 @@ class Engine:
         op.out_id = self._new_act((self.N, op.Ho, op.Wo, op.Cout), signed)
         op.res_id, op.res_signed = -1, False
         op.handle, op.w16 = None, None
+        op.variants = {}          # w16 -> (desc, GEMM-ready weight buffer, conv handle); created once, kept
+        op.wsig = op.bsig = None  # what was packed last (see _sig)
+        dev = self.device
+        op.wscale = torch.zeros(op.Cout, dtype=torch.float32, device=dev)
+        op.zf = torch.zeros(op.Cout, dtype=torch.float32, device=dev)
+        op.bias = torch.zeros(op.Cout, dtype=torch.float32, device=dev)
+        op.epi = {}
         return op
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _sig(*tensors):
+        """What identifies the CONTENT of parameter tensors without reading them: storage pointer,
+        autograd version counter (load_state_dict / any in-place op on the Parameter) and the write count
+        the quantizer entry points keep per storage (resnet.note_weight_write: writes through ``.data``)."""
+        import resnet
+        return tuple((t.data_ptr(), t._version, resnet.weight_write_count(t)) for t in tensors)
+
+    @staticmethod
+    def _bn_tensors(bn):
+        return (bn.weight, bn.bias, bn.running_mean, bn.running_var)
+
     def refresh_weights(self):
-        """Re-derives packed codes, GEMM-ready matrices, folded BN and conv handles from the
-        module tree's CURRENT fp32 parameters (content-derived, SURVEY.md H4 option b)."""
+        """Re-derives every layer from the module tree's CURRENT fp32 parameters."""
+        self.sync_weights(force=True)
+
+    def sync_weights(self, force=False):
+        """Brings the packed codes, GEMM-ready matrices and folded BN constants up to date with the module
+        tree (content-derived, SURVEY.md H4 option b) -- only for the layers whose parameter tensors were
+        written since they were packed last.  Device buffers keep their addresses (contents are updated in
+        place), so conv handles, tensor maps and captured CUDA graphs stay valid; the activation scales are
+        NOT touched (calibration is a separate, explicit step).  Returns the number of layers re-packed."""
+        import resnet
         lib, dev = self.lib, self.device
+        if self.epoch != resnet.WEIGHT_EPOCH[0]:
+            force = True
+            self.epoch = resnet.WEIGHT_EPOCH[0]
+        todo, bn_todo = [], []
+        for op in self.ops:
+            wsig = self._sig(op.conv.weight)
+            bsig = self._sig(*self._bn_tensors(op.bn))
+            if force or wsig != op.wsig:
+                todo.append((op, wsig, bsig))
+            elif bsig != op.bsig:
+                bn_todo.append((op, bsig))
+        ends_sig = self._sig(self.net.conv1.weight, *self._bn_tensors(self.net.bn1), self.net.fc.weight, self.net.fc.bias)
+        if not todo and not bn_todo and ends_sig == self.ends_sig and not force:
+            return 0
         with torch.cuda.device(dev), torch.no_grad():
             stream = L.current_stream(dev)
-            ws = [op.conv.weight.detach().reshape(op.Cout, -1).contiguous() for op in self.ops]
-            metas = classify_weights(ws, stream)
-            for op, w2d, (bit, z, s, bits_host) in zip(self.ops, ws, metas):
-                op.packed = encode_weight(w2d, bit, z, s, bits_host, stream)
-                op.bits_host = bits_host
-                w16 = 1 if int(bits_host.max()) > 8 else 0
-                desc = L.ConvDesc(self.N, op.H, op.W, op.Cin, op.Cout, op.k, op.k, op.stride, op.pad,
-                                  w16, self.impl, self.a_mode)
-                rows = lib.slq_gemm_weight_rows(ctypes.byref(desc))
-                op.wg = torch.empty((rows, op.k * op.k * op.Cin), dtype=torch.uint8, device=dev)
-                L.check(lib.slq_build_gemm_weights(ctypes.byref(desc), op.packed.blob.data_ptr(),
-                                                   op.packed.offsets.data_ptr(), op.packed.bits.data_ptr(),
-                                                   op.wg.data_ptr(), stream))
-                if op.handle is not None:
-                    lib.slq_conv_destroy(op.handle)
-                    op.handle = None
-                h = ctypes.c_void_p()
-                L.check(lib.slq_conv_create(ctypes.byref(desc), self.act[op.in_id].data_ptr(),
-                                            op.wg.data_ptr(), ctypes.byref(h)))
-                op.handle, op.w16, op.desc = h, w16, desc
-                a, b = self._fold_bn(op.bn)
-                op.wscale = (s * a).contiguous()
-                op.zf = z.to(torch.float32)
-                op.bias = b.contiguous()
-                op.epi = {}
-            self.stem_w = self.net.conv1.weight.detach().contiguous()
-            if self.stem is not None:
-                L.check(lib.slq_stem_set_weights(self.stem, self.stem_w.data_ptr(), stream))
-            self.stem_a, self.stem_b = self._fold_bn(self.net.bn1)
-            self.fc_w = self.net.fc.weight.detach().contiguous()
-            self.fc_b = self.net.fc.bias.detach().contiguous()
-        self.calibrated = False
-        self._graphs, self._seen = {}, set()
+            if todo:
+                ws = [op.conv.weight.detach().to(torch.float32).reshape(op.Cout, -1).contiguous() for op, _, _ in todo]
+                metas = classify_weights(ws, stream)
+                for (op, wsig, bsig), w2d, (bit, z, s, bits_host) in zip(todo, ws, metas):
+                    op.packed = encode_weight(w2d, bit, z, s, bits_host, stream)
+                    op.bits_host = bits_host
+                    w16 = 1 if int(bits_host.max()) > 8 else 0
+                    var = op.variants.get(w16)
+                    if var is None:  # first time this layer is seen in this mode: buffers + handle, kept for good
+                        desc = L.ConvDesc(self.N, op.H, op.W, op.Cin, op.Cout, op.k, op.k, op.stride, op.pad,
+                                          w16, self.impl, self.a_mode)
+                        rows = lib.slq_gemm_weight_rows(ctypes.byref(desc))
+                        wg = torch.empty((rows, op.k * op.k * op.Cin), dtype=torch.uint8, device=dev)
+                        h = ctypes.c_void_p()
+                        L.check(lib.slq_conv_create(ctypes.byref(desc), self.act[op.in_id].data_ptr(),
+                                                    wg.data_ptr(), ctypes.byref(h)))
+                        var = op.variants[w16] = (desc, wg, h)
+                    desc, wg, h = var
+                    L.check(lib.slq_build_gemm_weights(ctypes.byref(desc), op.packed.blob.data_ptr(),
+                                                       op.packed.offsets.data_ptr(), op.packed.bits.data_ptr(),
+                                                       wg.data_ptr(), stream))
+                    if op.w16 != w16:  # one-limb <-> two-limb: another kernel variant, graphs are stale
+                        self._graphs, self._seen = {}, set()
+                    op.handle, op.w16, op.desc, op.wg = h, w16, desc, wg
+                    op.s_dev, op.z_dev = s, z
+                    self._fold_into(op)
+                    op.wsig, op.bsig = wsig, bsig
+            for op, bsig in bn_todo:
+                self._fold_into(op)
+                op.bsig = bsig
+            if force or ends_sig != self.ends_sig:
+                self.stem_w.copy_(self.net.conv1.weight.detach())
+                if self.stem is not None:
+                    L.check(lib.slq_stem_set_weights(self.stem, self.stem_w.data_ptr(), stream))
+                a, b = self._fold_bn(self.net.bn1)
+                self.stem_a.copy_(a)
+                self.stem_b.copy_(b)
+                self.fc_w.copy_(self.net.fc.weight.detach())
+                self.fc_b.copy_(self.net.fc.bias.detach())
+                self.ends_sig = ends_sig
+        self.weights_version += 1
+        return len(todo)
+
+    def _fold_into(self, op):
+        """Per-channel epilogue constants of one layer, written IN PLACE (the epilogue descriptors and any
+        captured graph hold these addresses)."""
+        a, b = self._fold_bn(op.bn)
+        op.wscale.copy_(op.s_dev * a)
+        op.zf.copy_(op.z_dev.to(torch.float32))
+        op.bias.copy_(b)
 
     @staticmethod
     def _fold_bn(bn):
@@ -269,29 +342,42 @@ class Engine:
         self.in_kind = kind
         return x.contiguous()
 
-    def calibrate(self, x):
+    def calibrate(self, x, accumulate=False, headroom=1.0):
         """One pass with fp32 layer outputs: every activation tensor's static scale becomes
-        absmax/255 (u8) or absmax/127 (s8) of this batch.  Each layer is then launched again in its
-        quantised output mode, so the pass leaves exactly the bytes in HBM that forward(x) produces
-        (and every later layer is calibrated on what it will really see)."""
+        absmax/255 (u8) or absmax/127 (s8) of this batch, times ``headroom``; with ``accumulate`` the
+        larger of that and the scale it already has (running abs-max over several batches).  Each layer is
+        then launched again in its quantised output mode, so the pass leaves exactly the bytes in HBM that
+        forward(x) produces (and every later layer is calibrated on what it will really see)."""
         lib = self.lib
         x = self._check_x(x)
-        with torch.cuda.device(self.device):
+        if any(op.handle is None for op in self.ops):
+            raise RuntimeError("engine has no packed weights yet (call sync_weights())")
+        accumulate = accumulate and self.calibrated
+        with torch.cuda.device(self.device), torch.no_grad():
             st = L.current_stream(self.device)
             sc, tmp, f32 = self.act_scales.data_ptr(), self.absmax_tmp.data_ptr(), self.f32_scratch
+            old = self.act_scales.clone() if accumulate else None
+
+            def settle(idx):  # scale idx was just written by slq_absmax_scale
+                if headroom != 1.0:
+                    self.act_scales[idx:idx + 1].mul_(headroom)
+                if old is not None:
+                    torch.maximum(self.act_scales[idx:idx + 1], old[idx:idx + 1], out=self.act_scales[idx:idx + 1])
+
             n0 = self.act[0].numel()
             self._stem(x.data_ptr(), f32.data_ptr(), L.OUT_F32, st)
             L.check(lib.slq_absmax_scale(f32.data_ptr(), n0, sc, 0, 255, tmp, st))
+            settle(0)
             self._stem(x.data_ptr(), self.act[0].data_ptr(), L.OUT_U8, st)
             for op in self.ops:
                 n = op.M * op.Cout
                 L.check(lib.slq_conv_launch(op.handle, ctypes.byref(self._epilogue(op, L.OUT_F32, f32.data_ptr())), st))
                 L.check(lib.slq_absmax_scale(f32.data_ptr(), n, sc, op.out_id, 127 if op.signed else 255, tmp, st))
+                settle(op.out_id)
                 mode = L.OUT_S8 if op.signed else L.OUT_U8
                 e = self._epilogue(op, mode, self.act[op.out_id].data_ptr())
                 L.check(lib.slq_conv_launch(op.handle, ctypes.byref(e), st))
         self.calibrated = True
-        self._graphs, self._seen = {}, set()
 
     def forward(self, x):
         """Static-scale inference pass: stem -> conv launches -> tail.  Returns the engine's
@@ -378,9 +464,9 @@ class Engine:
     def __del__(self):
         try:
             for op in getattr(self, "ops", []):
-                if getattr(op, "handle", None) is not None:
-                    self.lib.slq_conv_destroy(op.handle)
-                    op.handle = None
+                for _desc, _wg, h in getattr(op, "variants", {}).values():
+                    self.lib.slq_conv_destroy(h)
+                op.variants, op.handle = {}, None
             if getattr(self, "stem", None) is not None:
                 self.lib.slq_stem_destroy(self.stem)
                 self.stem = None

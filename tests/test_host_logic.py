@@ -109,23 +109,49 @@ def test_module_tree_contract():
     net = resnet.resnet50(num_classes=1000)
     assert net.layer1[0].conv2.stride == (1, 1) and net.layer2[0].conv2.stride == (2, 2)  # v1.5
     assert net.layer2[0].conv1.stride == (1, 1) and net.layer2[0].downsample[0].stride == (2, 2)
+    v0 = net.layer1[0].conv1.weight._version
     net.load_state_dict(net.state_dict())
-    assert net._slq_dirty
+    assert net.layer1[0].conv1.weight._version > v0  # how the engine sees a reload (slq_engine.Engine._sig)
 
 
 def test_engine_invalidation_hooks(monkeypatch):
+    """What tells a compiled engine that a layer must be re-packed: the per-storage write
+    count kept by the quantizer entry points (writes through ``.data`` bump no version counter), the
+    Parameter's version (load_state_dict), the storage pointer (.to / .data = ...).  A no-op ``net.to()``
+    -- evaluate_acc_loss_softmax calls it before every evaluation -- must NOT invalidate anything."""
+    import copy
     import functions
     import resnet
+    import slq_engine
     cpu_standins.install(monkeypatch)
     net = resnet.resnet18(num_classes=10).eval()
     net._slq_dirty = False
-    e0 = resnet.WEIGHT_EPOCH[0]
-    net.layer1[0].conv1.weight.data = functions.channel_wise_quantizationperchan(net.layer1[0].conv1.weight.data, 8, 0)
-    assert resnet.WEIGHT_EPOCH[0] == e0 + 1
+    w = net.layer1[0].conv1.weight
+    other = net.layer1[0].conv2.weight
+    sig0, osig0 = slq_engine.Engine._sig(w), slq_engine.Engine._sig(other)
+    real_quantize_rows = functions.quantize_rows
+
+    def noting(tensor, rows, bits, **kw):  # the oracle stand-in + the product's own write note
+        out = real_quantize_rows(tensor, rows, bits, **kw)
+        resnet.note_weight_write(tensor)
+        return out
+    monkeypatch.setattr(functions, "quantize_rows", noting)
+    w.data = functions.channel_wise_quantizationperchan(w.data, 8, 0)
+    assert slq_engine.Engine._sig(w) != sig0 and slq_engine.Engine._sig(other) == osig0
     net.eval()
-    assert net._slq_dirty
-    net._slq_dirty = False
     net.to("cpu")
+    assert not net._slq_dirty              # nothing moved: engines, scales and graphs are kept
+    net.double()
+    assert net._slq_dirty                  # dtype conversion re-allocates every parameter
+    net.float()
+    sig1 = slq_engine.Engine._sig(w)
+    net.load_state_dict(net.state_dict())
+    assert slq_engine.Engine._sig(w) != sig1
+    net._slq_engines = {"x": object()}
+    twin = copy.deepcopy(net)              # engines hold ctypes handles: they are not copied
+    assert twin._slq_engines == {} and twin._slq_dirty
+    assert torch.equal(twin.layer1[0].conv1.weight, net.layer1[0].conv1.weight)
+    net.slq_invalidate()
     assert net._slq_dirty
 
 
