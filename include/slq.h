@@ -89,13 +89,41 @@ SLQ_API int slq_quantize_rows_host(float *w, int64_t n_rows, int64_t K, const in
                            uint8_t *codes, const int64_t *code_offsets, int32_t *z, float *s32,
                            int32_t *status);
 
+/* The same quantizer over a MULTI-TENSOR job table: one launch for every (row, bit) job of a whole model
+ * (resnet50_main.py:189-197 walks all 22,656 rows of the 48 quantised convs once per bit-width phase).
+ * jobs is a DEVICE array sorted by the caller into three classes, in this order:
+ *   n_small jobs with K <= 288, n_mid jobs with K <= 1152, n_large jobs with K <= 4608;
+ * every row pointer must be 16-byte aligned and K a multiple of 4 (rows that are not go through
+ * slq_quantize_rows).  z / s32 (may be NULL) / status are indexed like jobs.                         */
+typedef struct slq_qjob {
+  float *row;     /* device: K contiguous fp32, overwritten in place when write_back != 0          */
+  uint8_t *codes; /* device: where this row's packed codes go (slq_packed_row_bytes), or NULL     */
+  int32_t K;
+  int32_t bit;    /* 1..8 */
+} slq_qjob;
+SLQ_API int slq_quantize_jobs(const slq_qjob *jobs, int32_t n_small, int32_t n_mid, int32_t n_large,
+                              int32_t div_mode, int32_t write_back, int32_t *z, float *s32, int32_t *status,
+                              void *stream);
+
+/* Packed rows -> fp32: w[row, e] = fp32((code + z[row]) * s[row]).  For rows of <= 8 bits this is exactly the
+ * value the quantizer wrote back (functions.py:41: (round(w/scale + z) - z) * scale), so a packed snapshot
+ * restores a fake-quantised model bit for bit -- the device-resident replacement of the mains' undo buffer
+ * torch.save(net.state_dict()) / torch.load (resnet50_main.py:212, :233-234) and the loader of the packed
+ * on-disk format.  codes / code_offsets / bit / z / s as written by slq_quantize_rows or slq_encode_rows. */
+SLQ_API int slq_decode_rows(const uint8_t *codes, const int64_t *code_offsets, const int32_t *bit,
+                            const int32_t *z, const float *s, int64_t n_rows, int64_t K, float *w, void *stream);
+
 /* Content-derived classification used when the forward has to consume weights that were quantised
  * elsewhere (the mains mutate conv.weight.data and reload fp32 state_dicts):
  * for every row of w [n_rows, K] find the smallest bit in {2,4,6,8} whose affine grid (spanned by
  * the row's own min/max) already contains every element; rows that are on no such grid (never
- * quantised) get bit 16.  Writes bit/z/s per row.  No codes are produced here.                   */
+ * quantised) get bit 16.  Writes bit/z/s per row.  No codes are produced here.
+ * For rows of <= 8 bits the scale is then refined to the neighbouring float (within 2 ulp) for which
+ * fp32(rint(w / s) * s) == w holds for EVERY element, i.e. the scale the row was quantised with:
+ * exact[row] (may be NULL) = 1 when such a scale exists -- the packed row then decodes bit for bit
+ * (slq_decode_rows) -- else 0 (the row is still within 0.02 grid steps of the grid found).          */
 SLQ_API int slq_classify_rows(const float *w, int64_t n_rows, int64_t K, int32_t *bit, int32_t *z, float *s,
-                      void *stream);
+                      int32_t *exact, void *stream);
 
 /* Packs rows whose (bit, z, s) are already known (from slq_classify_rows): code = clamp(rint(w/s) - z).
  * Job j reads row j (all rows, in order).                                                        */
@@ -227,6 +255,34 @@ SLQ_API int slq_absmax_scale(const float *y, int64_t n, float *act_scales, int32
 /* out[i] = clamp(rint(y[i] / act_scales[id]), 0, 255)  (is_signed: clamp to [-127, 127], s8) */
 SLQ_API int slq_quantize_act(const float *y, int64_t n, const float *act_scales, int32_t id,
                      int32_t is_signed, uint8_t *out, void *stream);
+
+/* =============================================================================================
+ * 4. Evaluation tail (callers of the forward)
+ *    replaces  functions.py:109-122  output.max(1) + CrossEntropyLoss + Softmax, per batch
+ *              functions.py:142-146  KLdiv: a Python loop with one reduction per SAMPLE
+ * ============================================================================================= */
+
+/* logits [B, C] fp32 (device).  labels [B] int64 or NULL.  probs_out [B, C] or NULL: softmax(logits).
+ * ref_probs [B, C] or NULL: p of KL(p || softmax(logits)), i.e. the stored outputs of the un-quantised model.
+ * rows: scratch, 3*B floats.  accum: 4 doubles on the device, zeroed by the caller before the first batch:
+ *   accum[0] += number of argmax == label      accum[1] += batch-mean cross-entropy (one value per batch)
+ *   accum[2] += sum over the batch of KL_b      accum[3] += B
+ * Deterministic (fixed summation order); nothing is synchronised.                                      */
+SLQ_API int slq_eval_tail(const float *logits, const int64_t *labels, int32_t B, int32_t C, float *probs_out,
+                          const float *ref_probs, float *rows, double *accum, void *stream);
+/* KL(p || q) of two probability tensors [B, C]: accum[2] += sum_b sum_c p*log(p/q), accum[3] += B. */
+SLQ_API int slq_kl_rows(const float *p, const float *q, int32_t B, int32_t C, float *rows, double *accum,
+                        void *stream);
+
+/* =============================================================================================
+ * 5. Roofline probe
+ * ============================================================================================= */
+
+/* Enqueues, on every SM, `iters` (a multiple of 4) K blocks of back-to-back tcgen05.mma.kind::i8
+ * (M = 128, N = 256, K = 4 x 32, u8 x u8 -> s32) from two warps: the dense INT8 rate of this GPU, the
+ * denominator of the conv kernels' roofline fraction.  *ops_out (host, may be NULL) = 2 * MACs enqueued.
+ * The caller times the launch with CUDA events.                                                        */
+SLQ_API int slq_probe_i8_peak(int32_t iters, int64_t *ops_out, void *stream);
 
 #ifdef __cplusplus
 }

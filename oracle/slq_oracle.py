@@ -141,7 +141,7 @@ def encode_row(w):
         if s32 == 0 or not np.isfinite(np.float32(1.0) / s32):
             continue
         zd = float(np.rint(float(mn) / scale))
-        if abs(zd) > 1.0e6:
+        if abs(zd) > (8.0e6 if bit == 16 else 1.0e6):
             continue
         zf = np.float32(zd)
         t = (w / s32).astype(np.float32)
@@ -149,6 +149,17 @@ def encode_row(w):
         if bit != 16:
             if np.max(np.abs(t - r)) > ENCODE_TOL:
                 continue
+            # refinement (csrc/quantizer.cu classify_rows_kernel): the neighbouring scale, within 2 ulp, that
+            # reproduces every element exactly, fp32(rint(w / s) * s) == w
+            for delta in (0, -1, 1, -2, 2):
+                sc = (s32.view(np.int32) + np.int32(delta)).view(np.float32)
+                kmin = np.float32(np.rint(np.float32(mn / sc)))
+                k = np.rint((w / sc).astype(np.float32)).astype(np.float32)
+                c = (k - kmin).astype(np.float32)
+                if np.array_equal((k * sc).astype(np.float32), w) and c.min() >= 0 and c.max() <= levels \
+                        and abs(float(kmin)) <= 1.0e6:
+                    s32, zd, zf, r = sc, float(kmin), kmin, k
+                    break
         u = (r - zf).astype(np.float32)
         u = np.minimum(np.maximum(u, np.float32(0)), np.float32(levels))
         return bit, u.astype(np.int32), int(zd), s32

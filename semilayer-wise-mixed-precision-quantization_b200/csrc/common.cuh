@@ -40,7 +40,9 @@ void set_error(const char *fmt, ...);
     }                                                                                     \
   } while (0)
 
-int sm_count();  // cached multiprocessor count of the current device (148 on B200)
+constexpr int kMaxDevices = 64;
+int current_device();  // cudaGetDevice, 0 on error
+int sm_count();  // multiprocessor count of the current device (148 on B200), cached per device
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

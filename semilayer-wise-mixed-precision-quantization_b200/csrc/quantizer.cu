@@ -10,6 +10,8 @@
 // Data movement: a row (K <= 4608 fp32) is read from HBM exactly once into registers
 // (float4 loads, 32 threads per row for K <= 1152, 128 threads per row above), reduced for
 // min/max, transformed, and written once (fake-quant fp32 write-back + packed codes).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace slq {
@@ -21,17 +23,22 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
+int current_device() {
+  int dev = 0;
+  return cudaGetDevice(&dev) == cudaSuccess && dev >= 0 ? dev : 0;
+}
+int sm_count() {  // cached per device: a process may drive several GPUs
+  static int cached[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (dev >= kMaxDevices) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached[dev] = n;
     else
       return 148;
   }
-  return cached;
+  return cached[dev];
 }
 
 constexpr int kBlock = 128;  // threads per CTA for every quantizer kernel
@@ -92,7 +99,7 @@ __device__ __forceinline__ void store_codes4(uint8_t *row_codes, int64_t elem, i
 template <int GROUP>
 __device__ __forceinline__ void group_minmax(float &mn, float &mx, float *smem) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = (GROUP < 32 ? GROUP : 32) / 2; o > 0; o >>= 1) {  // xor offsets below GROUP stay inside the group
     mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
@@ -285,13 +292,15 @@ __global__ void __launch_bounds__(kBlock) classify_rows_kernel(const float *__re
                                                                int64_t K, int n_rows,
                                                                int32_t *__restrict__ bit_out,
                                                                int32_t *__restrict__ z_out,
-                                                               float *__restrict__ s_out) {
+                                                               float *__restrict__ s_out,
+                                                               int32_t *__restrict__ exact_out) {
   __shared__ float red[16];
   const int job = blockIdx.x * (kBlock / GROUP) + threadIdx.x / GROUP;
   if (GROUP == 32 && job >= n_rows) return;
   const int jobc = job < n_rows ? job : n_rows - 1;
   RowRegs<GROUP> r;
   r.load(w + (int64_t)jobc * K, K);
+  int res_exact = 0;
   float mn, mx;
   r.minmax(mn, mx);
   group_minmax<GROUP>(mn, mx, red);
@@ -314,7 +323,9 @@ __global__ void __launch_bounds__(kBlock) classify_rows_kernel(const float *__re
     const float inv = __fdiv_rn(1.0f, s32);
     if (s32 == 0.f || isinf(inv)) continue;
     const double zd = rint(__ddiv_rn((double)mn, scale));
-    if (fabs(zd) > 1.0e6) continue;
+    // |z| must stay exactly representable in the epilogue's fp32 arithmetic; the 16-bit grid of a
+    // never-quantised row may sit far from zero (narrow range around an offset), so it gets the full 2^23
+    if (fabs(zd) > (bit == 16 ? 8.0e6 : 1.0e6)) continue;
     int fail = 0;
     if (bit != 16) {
 #pragma unroll
@@ -336,6 +347,39 @@ __global__ void __launch_bounds__(kBlock) classify_rows_kernel(const float *__re
       res_z = (long long)zd;
       res_s = s32;
       found = true;
+      if (bit != 16) {
+        // Refinement: the scale re-derived from the row's own min/max can be an ulp or two off the scale
+        // the row was quantised with.  Look, among its nearest neighbours, for the scale that REPRODUCES
+        // every element exactly -- fp32(rint(w / s) * s) == w, functions.py:41's last two operations -- so
+        // that the packed row decodes bit for bit (slq_decode_rows: snapshots, packed files).
+        const int maxcode = (1 << bit) - 1;
+#pragma unroll 1
+        for (int d = 0; d < 5 && !res_exact; ++d) {
+          const int delta = d == 0 ? 0 : (d == 1 ? -1 : (d == 2 ? 1 : (d == 3 ? -2 : 2)));
+          const float sc = __int_as_float(__float_as_int(s32) + delta);
+          const float kmin = rintf(__fdiv_rn(mn, sc));
+          int bad = 0;
+#pragma unroll
+          for (int i = 0; i < kVpt; ++i) {
+            if (r.t + i * GROUP < r.nvec) {
+              const float e[4] = {r.v[i].x, r.v[i].y, r.v[i].z, r.v[i].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float k = rintf(__fdiv_rn(e[j], sc));
+                const float c = __fsub_rn(k, kmin);
+                bad |= !(__fmul_rn(k, sc) == e[j]) || c < 0.f || c > (float)maxcode;
+              }
+            }
+          }
+          bad = __any_sync(0xffffffffu, bad);
+          if (GROUP > 32) bad = __syncthreads_or(bad);
+          if (!bad && fabsf(kmin) <= 1.0e6f) {
+            res_s = sc;
+            res_z = (long long)kmin;
+            res_exact = 1;
+          }
+        }
+      }
     }
   }
   if (!found) {  // degenerate (denormal) range: treat as the constant mn
@@ -348,6 +392,7 @@ __global__ void __launch_bounds__(kBlock) classify_rows_kernel(const float *__re
     bit_out[job] = res_bit;
     z_out[job] = (int32_t)res_z;
     s_out[job] = res_s;
+    if (exact_out) exact_out[job] = res_exact;
   }
 }
 
@@ -380,6 +425,129 @@ __global__ void __launch_bounds__(kBlock) encode_rows_kernel(
         u[j] = (int)fminf(fmaxf(__fsub_rn(k, zf), 0.f), maxc);
       }
       store_codes4(row_codes, (int64_t)idx * 4, K, bit, u);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1m: the same quantizer over a MULTI-TENSOR job table (slq_quantize_jobs): every job names its own row
+// pointer, length and code destination, so ALL layers of a model are one launch (the reference issues
+// 7 launches + 2 syncs per row, functions.py:35-41; resnet50_main.py:189-197 walks 22,656 rows per phase).
+// Jobs are sorted by the caller into three classes, which are three block ranges of one grid:
+//   K <= 288  : 8 lanes per row, 16 rows per CTA   (K = 64 / 128 / 256: a whole warp per row left 50-75 %
+//               of its lanes without a float4 to load)
+//   K <= 1152 : one warp per row, 4 rows per CTA
+//   K <= 4608 : one CTA per row
+// No early exits below warp granularity: sub-warp groups share shuffles and ballots.
+// ------------------------------------------------------------------------------------------
+template <int GROUP, int DIV>
+__device__ __forceinline__ void quantize_job(const slq_qjob &jb, bool active, int job, int write_back,
+                                             int32_t *__restrict__ z_out, float *__restrict__ s_out,
+                                             int32_t *__restrict__ status, float *red) {
+  const int64_t K = jb.K;
+  float *row = jb.row;
+  const int bit = jb.bit;
+  RowRegs<GROUP> r;
+  r.load(row, K);
+  float mn, mx;
+  r.minmax(mn, mx);
+  group_minmax<GROUP>(mn, mx, red);
+  const Affine a = derive_affine(mn, mx, bit);
+  const bool leader = (threadIdx.x % GROUP) == 0;
+  const bool go = active && a.ok;
+  const int maxcode = (1 << bit) - 1;
+  uint8_t *row_codes = jb.codes;
+  float4 *out4 = reinterpret_cast<float4 *>(row);
+  int bad = 0;
+  if (go) {
+#pragma unroll
+    for (int i = 0; i < kVpt; ++i) {
+      const int idx = r.t + i * GROUP;
+      if (idx < r.nvec) {
+        float t3[4];
+        float4 q;
+        q.x = fake_quant<DIV>(r.v[i].x, a.s32, a.inv, a.zf, &t3[0]);
+        q.y = fake_quant<DIV>(r.v[i].y, a.s32, a.inv, a.zf, &t3[1]);
+        q.z = fake_quant<DIV>(r.v[i].z, a.s32, a.inv, a.zf, &t3[2]);
+        q.w = fake_quant<DIV>(r.v[i].w, a.s32, a.inv, a.zf, &t3[3]);
+        if (write_back) out4[idx] = q;
+        if (row_codes) {
+          int u[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            long long c = (long long)t3[e] - 2 * a.z;
+            if (c < 0) { c = 0; bad = 1; }
+            if (c > maxcode) { c = maxcode; bad = 1; }
+            u[e] = (int)c;
+          }
+          store_codes4(row_codes, (int64_t)idx * 4, K, bit, u);
+        }
+      }
+    }
+  }
+  if (GROUP <= 32) {
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(unsigned)(GROUP - 1)));
+    bad = (__ballot_sync(0xffffffffu, bad) & gmask) != 0;
+  } else {
+    bad = __syncthreads_or(bad);
+  }
+  if (leader && active) {
+    status[job] = !a.ok ? SLQ_ROW_ZERO_RANGE : (bad ? SLQ_ROW_CODE_RANGE : SLQ_ROW_OK);
+    if (z_out) z_out[job] = a.ok ? (int32_t)a.z : 0;
+    if (s_out) s_out[job] = a.ok ? a.s32 : 0.f;
+  }
+}
+
+template <int DIV>
+__global__ void __launch_bounds__(kBlock) quantize_jobs_kernel(const slq_qjob *__restrict__ jobs, int n_small,
+                                                               int n_mid, int n_large, int blocks_small,
+                                                               int blocks_mid, int write_back,
+                                                               int32_t *__restrict__ z_out, float *__restrict__ s_out,
+                                                               int32_t *__restrict__ status) {
+  __shared__ float red[16];
+  const int b = blockIdx.x;
+  if (b < blocks_small) {
+    const int job = b * (kBlock / 8) + threadIdx.x / 8;
+    const bool active = job < n_small;
+    quantize_job<8, DIV>(jobs[active ? job : n_small - 1], active, job, write_back, z_out, s_out, status, red);
+  } else if (b < blocks_small + blocks_mid) {
+    const int j = (b - blocks_small) * (kBlock / 32) + threadIdx.x / 32;
+    const bool active = j < n_mid;
+    const int job = n_small + j;
+    quantize_job<32, DIV>(jobs[active ? job : n_small + n_mid - 1], active, job, write_back, z_out, s_out, status, red);
+  } else {
+    const int job = n_small + n_mid + (b - blocks_small - blocks_mid);
+    quantize_job<128, DIV>(jobs[job], true, job, write_back, z_out, s_out, status, red);
+  }
+}
+
+// K4: packed codes -> fp32 rows, w = fp32((code + z) * s): the exact inverse of the quantizer's write-back
+// for rows of <= 8 bits ((code + z) is the integer level k of functions.py:41, k * scale is its last op).
+__global__ void __launch_bounds__(256) decode_rows_kernel(const uint8_t *__restrict__ codes,
+                                                          const int64_t *__restrict__ code_offsets,
+                                                          const int32_t *__restrict__ bit_in,
+                                                          const int32_t *__restrict__ z_in,
+                                                          const float *__restrict__ s_in, int n_rows, int64_t K,
+                                                          float *__restrict__ w) {
+  const int64_t kq = (K + 3) >> 2;
+  const int64_t total = (int64_t)n_rows * kq;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / kq);
+    const int64_t e0 = (idx % kq) * 4;
+    const int bit = bit_in[row];
+    const float zf = (float)z_in[row], s = s_in[row];
+    const uint8_t *src = codes + code_offsets[row];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t e = e0 + j;
+      if (e >= K) break;
+      int c;
+      if (bit == 4) c = (src[e >> 1] >> ((e & 1) * 4)) & 15;
+      else if (bit == 2) c = (src[e >> 2] >> ((e & 3) * 2)) & 3;
+      else if (bit == 16) c = (int)src[e] | ((int)src[K + e] << 8);
+      else c = src[e];
+      w[(int64_t)row * K + e] = __fmul_rn(__fadd_rn((float)c, zf), s);
     }
   }
 }
@@ -550,14 +718,14 @@ extern "C" int slq_quantize_rows_host(float *w, int64_t n_rows, int64_t K, const
 }
 
 extern "C" int slq_classify_rows(const float *w, int64_t n_rows, int64_t K, int32_t *bit,
-                                 int32_t *z, float *s, void *stream) {
+                                 int32_t *z, float *s, int32_t *exact, void *stream) {
   SLQ_CHECK_ARG(w && bit && z && s, "slq_classify_rows: null pointer argument");
   SLQ_CHECK_ARG(K > 0 && n_rows > 0, "slq_classify_rows: empty problem");
   cudaStream_t st = (cudaStream_t)stream;
   if (fast_path_ok(w, K, 32))
-    classify_rows_kernel<32><<<(unsigned)ceil_div(n_rows, 4), kBlock, 0, st>>>(w, K, (int)n_rows, bit, z, s);
+    classify_rows_kernel<32><<<(unsigned)ceil_div(n_rows, 4), kBlock, 0, st>>>(w, K, (int)n_rows, bit, z, s, exact);
   else if (fast_path_ok(w, K, 128))
-    classify_rows_kernel<128><<<(unsigned)n_rows, kBlock, 0, st>>>(w, K, (int)n_rows, bit, z, s);
+    classify_rows_kernel<128><<<(unsigned)n_rows, kBlock, 0, st>>>(w, K, (int)n_rows, bit, z, s, exact);
   else {
     set_error("slq_classify_rows: K=%lld unsupported (need K %% 4 == 0, K <= 4608, 16B-aligned)", (long long)K);
     return SLQ_ERR_UNSUPPORTED;
@@ -580,6 +748,39 @@ extern "C" int slq_encode_rows(const float *w, int64_t n_rows, int64_t K, const 
     set_error("slq_encode_rows: K=%lld unsupported (need K %% 4 == 0, K <= 4608, 16B-aligned)", (long long)K);
     return SLQ_ERR_UNSUPPORTED;
   }
+  SLQ_LAUNCH_CHECK();
+  return SLQ_OK;
+}
+
+
+extern "C" int slq_quantize_jobs(const slq_qjob *jobs, int32_t n_small, int32_t n_mid, int32_t n_large,
+                                 int32_t div_mode, int32_t write_back, int32_t *z, float *s32,
+                                 int32_t *status, void *stream) {
+  SLQ_CHECK_ARG(jobs && status, "slq_quantize_jobs: null pointer argument");
+  SLQ_CHECK_ARG(n_small >= 0 && n_mid >= 0 && n_large >= 0, "slq_quantize_jobs: negative job count");
+  SLQ_CHECK_ARG(div_mode == SLQ_DIV_TRUE || div_mode == SLQ_DIV_RECIP, "slq_quantize_jobs: div_mode %d", div_mode);
+  const int blocks_small = (int)ceil_div(n_small, kBlock / 8), blocks_mid = (int)ceil_div(n_mid, kBlock / 32);
+  const int64_t grid = (int64_t)blocks_small + blocks_mid + n_large;
+  if (grid == 0) return SLQ_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (div_mode == SLQ_DIV_TRUE)
+    quantize_jobs_kernel<SLQ_DIV_TRUE><<<(unsigned)grid, kBlock, 0, st>>>(jobs, n_small, n_mid, n_large, blocks_small,
+                                                                        blocks_mid, write_back, z, s32, status);
+  else
+    quantize_jobs_kernel<SLQ_DIV_RECIP><<<(unsigned)grid, kBlock, 0, st>>>(jobs, n_small, n_mid, n_large, blocks_small,
+                                                                         blocks_mid, write_back, z, s32, status);
+  SLQ_LAUNCH_CHECK();
+  return SLQ_OK;
+}
+
+extern "C" int slq_decode_rows(const uint8_t *codes, const int64_t *code_offsets, const int32_t *bit,
+                               const int32_t *z, const float *s, int64_t n_rows, int64_t K, float *w,
+                               void *stream) {
+  SLQ_CHECK_ARG(codes && code_offsets && bit && z && s && w, "slq_decode_rows: null pointer argument");
+  SLQ_CHECK_ARG(K > 0 && n_rows > 0, "slq_decode_rows: empty problem");
+  const int64_t total = n_rows * ((K + 3) / 4);
+  const int blocks = (int)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+  decode_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(codes, code_offsets, bit, z, s, (int)n_rows, K, w);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }

@@ -10,8 +10,11 @@ Same ten module-level entry points, same argument meaning, return values and err
                                                     candidates sharded over torch.distributed ranks)
   make_quantizedlists                               reference functions.py:590-612
 
-Extensions (not in the reference): ``quantize_rows`` (a whole semilayer / layer in one launch,
-returns the packed codes) and ``make_semilayers`` (arch-generic sweep, optional delta-loss metric).
+Extensions (not in the reference): ``quantize_rows`` (a whole semilayer / layer in one launch, returns the
+packed codes), ``quantize_model`` (every layer of a model in one launch), ``make_semilayers`` (arch-generic
+sweep, optional delta-loss metric), ``snapshot`` / ``restore`` (device-resident undo state instead of
+torch.save / torch.load), ``save_packed`` / ``load_packed`` (packed model file) and
+``make_deltaloss_table`` / ``write_deltaloss_csv`` (regenerates dataset/*_deltaloss.csv).
 """
 import os
 
@@ -145,45 +148,188 @@ def channel_wise_quantizationperchan(tensor, bit, i):
     return tensor
 
 
+class PackedModel:
+    """Result of quantize_model: all jobs of all tensors in ONE launch.  Arrays are in launch order (jobs
+    sorted by row length class); ``perm[j]`` is the position of launch-order job j in the caller's order
+    (tensors in the order given, rows in the order given)."""
+
+    def __init__(self, perm, item_of, rows, bits, K, offsets, blob, z, s32, status):
+        self.perm, self.item_of, self.rows, self.bits, self.K = perm, item_of, rows, bits, K
+        self.offsets, self.blob, self.z, self.s32, self.status = offsets, blob, z, s32, status
+
+    @property
+    def nbytes(self):
+        return 0 if self.blob is None else int(self.blob.numel())
+
+    def check(self):
+        """The one synchronisation: raises ZeroDivisionError like the reference (functions.py:40) if any
+        row was constant."""
+        st = self.status.cpu()
+        if bool((st & L.ROW_ZERO_RANGE).any()):
+            raise ZeroDivisionError("float division by zero")
+        return st
+
+
+_QJOB = np.dtype([("row", "<u8"), ("codes", "<u8"), ("K", "<i4"), ("bit", "<i4")])
+
+
+def quantize_model(items, write_back=True, want_codes=True, div_mode=None, check=True):
+    """Quantises rows of SEVERAL weight tensors -- a whole model's bit assignment -- in ONE kernel launch
+    (slq_quantize_jobs): ``items`` is a list of ``(tensor, rows, bits)`` with contiguous fp32 CUDA tensors
+    ``[Cout, ...]`` on one device.  The reference makes one quantize_wgt call (7 launches, 2 syncs) per row
+    (resnet50_main.py:189-197).  One host->device copy of the job table, one launch, and -- with ``check`` --
+    one synchronisation at the end.  Returns PackedModel."""
+    lib = L.lib()
+    if not items:
+        raise ValueError("quantize_model: no tensors")
+    dev = items[0][0].device
+    rowp, Ks, bits_all, rows_all, item_of = [], [], [], [], []
+    for i, (t, rows, bits) in enumerate(items):
+        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda or t.device != dev:
+            raise TypeError("quantize_model needs contiguous float32 CUDA tensors on one device")
+        K = t[0].numel()
+        if K % 4 != 0 or K > 4608 or t.data_ptr() % 16 != 0:
+            raise ValueError("quantize_model: row length %d unsupported (use quantize_rows)" % K)
+        r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
+        b = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)
+        if r.size != b.size:
+            raise ValueError("rows and bits must have the same length")
+        if r.size and (r.min() < 0 or r.max() >= t.shape[0]):
+            raise IndexError("row index out of range")
+        if b.size and (b.min() < 1 or b.max() > 8):
+            raise ValueError("bit-width must be in 1..8")
+        rowp.append(np.uint64(t.data_ptr()) + (r * (4 * K)).astype(np.uint64))
+        Ks.append(np.full(r.size, K, np.int32))
+        bits_all.append(b)
+        rows_all.append(r)
+        item_of.append(np.full(r.size, i, np.int32))
+    rowp, Ks, bits_all = np.concatenate(rowp), np.concatenate(Ks), np.concatenate(bits_all)
+    rows_all, item_of = np.concatenate(rows_all), np.concatenate(item_of)
+    n = rowp.size
+    if n == 0:
+        raise ValueError("quantize_model: no rows")
+    cls = (Ks > 288).astype(np.int8) + (Ks > 1152).astype(np.int8)
+    perm = np.argsort(cls, kind="stable")
+    counts = np.bincount(cls, minlength=3)
+    sizes = (np.where(bits_all == 4, (Ks + 1) // 2, np.where(bits_all == 2, (Ks + 3) // 4, Ks)).astype(np.int64) + 15) // 16 * 16
+    sizes_p = sizes[perm]
+    offs = np.zeros(n, np.int64)
+    offs[1:] = np.cumsum(sizes_p)[:-1]
+    dm = _div_mode_for(items[0][0], div_mode)
+    with torch.cuda.device(dev):
+        blob = torch.empty(max(int(sizes_p.sum()), 16), dtype=torch.uint8, device=dev) if want_codes else None
+        jobs = np.empty(n, _QJOB)
+        jobs["row"], jobs["K"], jobs["bit"] = rowp[perm], Ks[perm], bits_all[perm]
+        jobs["codes"] = (np.uint64(blob.data_ptr()) + offs.astype(np.uint64)) if want_codes else 0
+        jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
+        z = torch.empty(n, dtype=torch.int32, device=dev)
+        s32 = torch.empty(n, dtype=torch.float32, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        L.check(lib.slq_quantize_jobs(jobs_d.data_ptr(), int(counts[0]), int(counts[1]), int(counts[2]), dm,
+                                      1 if write_back else 0, z.data_ptr(), s32.data_ptr(), status.data_ptr(),
+                                      L.current_stream(dev)))
+    if write_back:
+        for t, _r, _b in items:
+            resnet.note_weight_write(t)
+    pm = PackedModel(perm, item_of[perm], rows_all[perm], bits_all[perm], Ks[perm], offs, blob, z, s32, status)
+    pm._keepalive = jobs_d  # the kernel reads the table asynchronously
+    if check:
+        pm.check()
+    return pm
+
+
 # ==============================================================================================
 # evaluation (callers of the forward)
 # ==============================================================================================
-def evaluate_loss(net, device, data_loader):
-    """Mean-of-batch-means cross-entropy (reference functions.py:45-82; unused by the mains)."""
+def _fused_tail_ok(t):
+    return torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()
+
+
+def _evaluate(net, device, data_loader, ref_outputs=None, want_probs=True):
+    """One pass over the loader: -> (acc, loss, [softmax per batch], KL(ref_outputs || outputs) or None).
+
+    On CUDA the whole tail of every batch -- argmax, cross-entropy, softmax and, when ``ref_outputs`` (the
+    stored softmax outputs of the un-quantised model) is given, the per-sample KL divergence -- is ONE fused
+    kernel pass (slq_eval_tail) that accumulates into four doubles on the device; they are read back ONCE
+    at the end (the reference synchronises three times per evaluation, functions.py:129, and KLdiv loops
+    over every sample in Python, functions.py:142-146).  CPU tensors take the stock-torch route."""
+    net.to(device)
     net.eval()
+    lib = None
+    accum = None
+    labels, preds, outputs = [], [], []
+    loss_sum, count, n_img = 0, 0, 0
+    kl_sum, kl_n = None, 0
     criterion = torch.nn.CrossEntropyLoss()
-    total, count = 0, 0
-    for x, y in data_loader:
+    for bi, (x, y) in enumerate(data_loader):
         x, y = x.to(device), y.to(device)
         with torch.no_grad():
-            total = total + criterion(net(x), y)
+            out = net(x)
+        ref = ref_outputs[bi] if ref_outputs is not None else None
+        if _fused_tail_ok(out) and (ref is None or (_fused_tail_ok(ref) and ref.shape == out.shape)):
+            if accum is None:
+                lib = L.lib()
+                accum = torch.zeros(4, dtype=torch.float64, device=out.device)
+            B, C = out.shape
+            y64 = y.to(torch.int64).contiguous()
+            probs = torch.empty_like(out) if want_probs else None
+            rows = torch.empty(3 * B, dtype=torch.float32, device=out.device)
+            with torch.cuda.device(out.device):
+                L.check(lib.slq_eval_tail(out.data_ptr(), y64.data_ptr(), B, C, L.ptr(probs), L.ptr(ref),
+                                          rows.data_ptr(), accum.data_ptr(), L.current_stream(out.device)))
+            outputs.append(probs)
+            n_img += B
+        else:  # stock torch ops, exactly the reference's sequence
+            with torch.no_grad():
+                preds.append(out.max(1)[1])
+                loss_sum = loss_sum + criterion(out, y)
+                p = torch.softmax(out, dim=1)
+                outputs.append(p)
+                if ref is not None:
+                    kl = (ref * (ref / p).log()).sum(dim=1)
+                    kl_sum = kl.sum() if kl_sum is None else kl_sum + kl.sum()
+                    kl_n += kl.numel()
+            labels.append(y)
         count += 1
-    return (total / count).item()
+    if accum is not None:
+        if labels:
+            raise RuntimeError("evaluate: the loader mixed CUDA and host batches")
+        a = accum.cpu().numpy()  # the one device->host read of the evaluation
+        acc = float(np.float32(a[0]) / np.float32(n_img))
+        loss = float(np.float32(a[1]) / np.float32(count))
+        kl = float(np.float32(a[2] / a[3])) if ref_outputs is not None else None
+        return acc, loss, outputs, kl
+    labels, preds = torch.cat(labels), torch.cat(preds)
+    acc = (labels == preds).float().sum() / len(labels)
+    kl = (kl_sum / kl_n).item() if kl_sum is not None else None
+    return acc.item(), (loss_sum / count).item(), outputs, kl
+
+
+def evaluate_loss(net, device, data_loader):
+    """Mean-of-batch-means cross-entropy (reference functions.py:45-82; unused by the mains)."""
+    return _evaluate(net, device, data_loader, want_probs=False)[1]
 
 
 def evaluate_acc_loss_softmax(net, device, data_loader):
     """-> (accuracy, mean-of-batch-means CE loss, [softmax per batch])  (reference functions.py:84-129)."""
-    net.to(device)
-    net.eval()
-    criterion = torch.nn.CrossEntropyLoss()
-    labels, preds, outputs = [], [], []
-    loss_sum, count = 0, 0
-    for x, y in data_loader:
-        x, y = x.to(device), y.to(device)
-        with torch.no_grad():
-            out = net(x)
-            preds.append(out.max(1)[1])
-            loss_sum = loss_sum + criterion(out, y)
-            outputs.append(torch.softmax(out, dim=1))
-        labels.append(y)
-        count += 1
-    labels, preds = torch.cat(labels), torch.cat(preds)
-    acc = (labels == preds).float().sum() / len(labels)
-    return acc.item(), (loss_sum / count).item(), outputs
+    acc, loss, outputs, _kl = _evaluate(net, device, data_loader)
+    return acc, loss, outputs
 
 
 def KLdiv(n_out, out):
     """Mean over samples of sum_c p*log(p/q), p = before, q = after (reference functions.py:131-149)."""
+    if len(out) and all(_fused_tail_ok(p) and _fused_tail_ok(q) and p.shape == q.shape for p, q in zip(n_out, out)):
+        lib = L.lib()
+        dev = out[0].device
+        accum = torch.zeros(4, dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            for p, q in zip(n_out, out):
+                B, C = q.shape
+                rows = torch.empty(3 * B, dtype=torch.float32, device=dev)
+                L.check(lib.slq_kl_rows(p.data_ptr(), q.data_ptr(), B, C, rows.data_ptr(), accum.data_ptr(),
+                                        L.current_stream(dev)))
+        a = accum.cpu().numpy()
+        return float(np.float32(a[2] / a[3]))
     total, n = None, 0
     for p, q in zip(n_out, out):
         kl = (p * (p / q).log()).sum(dim=1)
@@ -232,21 +378,8 @@ def _dist():
     return None, 0, 1
 
 
-def make_semilayers(arch, net, device, originaloutputs, listminus, listplus, metric=None, shard=True):
-    """Sensitivity sweep (reference functions.py:186-588, three copies): one candidate per semilayer
-    = quantise its channels on fresh weights, evaluate the whole loader, sensitivity =
-    KL(before, after) / sum(numel * (32-bit)/32).
-
-    Candidates are independent, so with torch.distributed initialised they are dealt round-robin
-    to the ranks and the per-candidate values are exchanged with ONE all_gather (SURVEY.md 8e);
-    every rank returns the full ``(semilayers, orders)``.
-    metric: 'kl' (reference) or 'dloss' (loss_candidate - loss_base; KL is NaN for random-init
-    R34/R50).  Default from $SLQ_SWEEP_METRIC, else 'kl'."""
-    metric = metric or os.environ.get("SLQ_SWEEP_METRIC", "kl")
-    dist, rank, world = _dist() if shard else (None, 0, 1)
-    listminus.append(list(SENTINEL))  # the reference mutates the caller's lists the same way
-    listplus.append(list(SENTINEL))
-    # ---- pure bookkeeping: candidates = runs of equal layer number inside each list ------------
+def _semilayer_runs(listminus, listplus):
+    """Candidates = runs of equal layer number inside each (sentinel-terminated) list."""
     semilayers = []
     for lst in (listminus, listplus):
         cur = []
@@ -257,47 +390,110 @@ def make_semilayers(arch, net, device, originaloutputs, listminus, listplus, met
             if row[2] != lst[i + 1][2]:
                 semilayers.append(cur)
                 cur = []
+    return semilayers
+
+
+def _gather_values(values, flags, dist, world):
+    """ONE all_gather of [values | error flags]; entry i comes from its owner rank i % world."""
+    both = torch.cat([values, flags])
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    bufs = [torch.zeros_like(both, device=dev) for _ in range(world)]
+    dist.all_gather(bufs, both.to(dev))
+    n = values.numel()
+    for index in range(n):
+        src = bufs[index % world].cpu()
+        values[index] = src[index]
+        flags[index] = src[n + index]
+    # a rank may also have failed outside its own candidates (candidate 0 runs everywhere)
+    for src in bufs:
+        flags[:] = torch.maximum(flags, src.cpu()[n:])
+
+
+def make_semilayers(arch, net, device, originaloutputs, listminus, listplus, metric=None, shard=True):
+    """Sensitivity sweep (reference functions.py:186-588, three copies): one candidate per semilayer
+    = quantise its channels on fresh pretrained weights, evaluate the whole loader, sensitivity =
+    KL(before, after) / sum(numel * (32-bit)/32).
+
+    Candidates are independent, so with torch.distributed initialised they are dealt round-robin
+    to the ranks and the per-candidate values are exchanged with ONE all_gather (SURVEY.md 8e);
+    every rank returns the full ``(semilayers, orders)``.
+
+    "Fresh pretrained weights" (the reference builds a new ``resnetXX(pretrained='imagenet')`` per candidate,
+    functions.py:258/393/528) is ONE work model per call here: the candidate's conv tensors are saved on the
+    device, quantised in place, evaluated and restored, so a candidate costs its forward passes plus the
+    re-packing of the one or two layers it touched; the work model shares the caller's activation scales.
+    Candidate 0 runs on the CALLER's net object and mutates it (reference quirk Q3), on every rank.
+
+    metric: 'kl' (reference) or 'dloss' (loss_candidate - loss_base; KL is NaN for random-init
+    R34/R50).  Default from $SLQ_SWEEP_METRIC, else 'kl'.
+    A candidate that raises (e.g. ZeroDivisionError for a constant channel) does not strand the other ranks
+    in the collective: the error is flagged, every rank reaches the all_gather, then every rank raises."""
+    metric = metric or os.environ.get("SLQ_SWEEP_METRIC", "kl")
+    dist, rank, world = _dist() if shard else (None, 0, 1)
+    listminus.append(list(SENTINEL))  # the reference mutates the caller's lists the same way
+    listplus.append(list(SENTINEL))
+    semilayers = _semilayer_runs(listminus, listplus)
     factory = getattr(resnet, arch)
     # delta-loss needs the un-quantised loss from logits (the stored softmax underflows to exact zeros on
     # random-init R34/R50, which is what makes KL NaN there): one more evaluation of the caller's net,
     # before candidate 0 mutates it
-    base = evaluate_acc_loss_softmax(net, device, imagenet.val_loader)[1] if metric == "dloss" else None
+    base = _evaluate(net, device, imagenet.val_loader, want_probs=False)[1] if metric == "dloss" else None
     values = torch.zeros(len(semilayers), dtype=torch.float64)
+    flags = torch.zeros(len(semilayers), dtype=torch.float64)
+    work, first_error = None, None
     for index, rows in enumerate(semilayers):
         mine = (index % world) == rank
         if not mine and index != 0:
             continue
-        # candidate 0 runs on the CALLER's net object and mutates it (reference quirk Q3); every
-        # other candidate gets a fresh 'pretrained' model (functions.py:258/393/528)
-        cand = net if index == 0 else factory(num_classes=1000, pretrained='imagenet')
-        layers = [cand.layer1, cand.layer2, cand.layer3, cand.layer4]
-        param = 0.0
-        by_conv = {}
-        for li, bi, lnum, cnum, w_bit, _flag, _sel, _gi in rows:
-            conv = _conv_of(arch, layers[li][bi], lnum)
-            by_conv.setdefault(id(conv), (conv, [], []))
-            by_conv[id(conv)][1].append(cnum)
-            by_conv[id(conv)][2].append(w_bit)
-            param += conv.weight[cnum].data.numel() * ((32 - w_bit) / 32)
-        for conv, chans, bits in by_conv.values():
-            # a semilayer's rows are distinct channels of one conv: one launch, same result as the
-            # reference's per-channel loop
-            conv.weight.data = _quantize_channels(conv.weight.data, chans, bits)
-        if not mine:
-            continue
-        acc, loss, after = evaluate_acc_loss_softmax(cand, device, imagenet.val_loader)
-        val = (loss - base) if metric == "dloss" else KLdiv(originaloutputs, after) / param
-        values[index] = val
-        print(rows[0][4], 'bit', 'semilayer-No.', index, 'layernumber=', rows[0][2], 'channels=', len(rows),
-              'total KL divergence=' if metric == "kl" else 'delta loss=', val)
+        saved = []
+        try:
+            if index == 0:
+                cand = net
+            else:
+                if work is None:
+                    work = factory(num_classes=1000, pretrained='imagenet')
+                    if hasattr(work, "slq_share_calibration"):
+                        work.slq_share_calibration(net)
+                    work.to(device)
+                cand = work
+            layers = [cand.layer1, cand.layer2, cand.layer3, cand.layer4]
+            param = 0.0
+            by_conv = {}
+            for li, bi, lnum, cnum, w_bit, _flag, _sel, _gi in rows:
+                conv = _conv_of(arch, layers[li][bi], lnum)
+                by_conv.setdefault(id(conv), (conv, [], []))
+                by_conv[id(conv)][1].append(cnum)
+                by_conv[id(conv)][2].append(w_bit)
+                param += conv.weight[cnum].data.numel() * ((32 - w_bit) / 32)
+            for conv, chans, bits in by_conv.values():
+                if cand is work:
+                    saved.append((conv, conv.weight.data.clone()))
+                # a semilayer's rows are distinct channels of one conv: one launch, same result as the
+                # reference's per-channel loop
+                conv.weight.data = _quantize_channels(conv.weight.data, chans, bits)
+            if mine:
+                want_kl = metric == "kl"
+                _acc, loss, _after, kl = _evaluate(cand, device, imagenet.val_loader,
+                                                   ref_outputs=originaloutputs if want_kl else None,
+                                                   want_probs=False)
+                val = (loss - base) if metric == "dloss" else kl / param
+                values[index] = val
+                print(rows[0][4], 'bit', 'semilayer-No.', index, 'layernumber=', rows[0][2], 'channels=', len(rows),
+                      'total KL divergence=' if metric == "kl" else 'delta loss=', val)
+        except Exception as e:  # keep walking: the collective below must be reached by every rank
+            flags[index] = 1.0
+            first_error = first_error or e
+        finally:
+            for conv, orig in saved:  # back to the pretrained weights for the next candidate
+                conv.weight.data.copy_(orig)
+                resnet.note_weight_write(conv.weight.data)
     if world > 1:
-        gathered = [torch.zeros_like(values) for _ in range(world)]
-        pad = values.clone()
-        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-        bufs = [g.to(dev) for g in gathered]
-        dist.all_gather(bufs, pad.to(dev))
-        for index in range(len(semilayers)):
-            values[index] = bufs[index % world][index].cpu()
+        _gather_values(values, flags, dist, world)
+    if bool(flags.any()):
+        bad = [int(i) for i in flags.nonzero().flatten()]
+        if first_error is not None:
+            raise first_error
+        raise RuntimeError("sensitivity sweep: candidates %s failed on another rank" % bad)
     orders = [[i, float(values[i])] for i in range(len(semilayers))]
     return semilayers, orders
 
@@ -321,6 +517,106 @@ def make_semilayers_resnet34(net, device, originaloutputs, listminus, listplus):
 
 def make_semilayers_resnet50(net, device, originaloutputs, listminus, listplus):
     return make_semilayers("resnet50", net, device, originaloutputs, listminus, listplus)
+
+
+# ==============================================================================================
+# accept / undo state and the packed model format (N2, N4)
+# ==============================================================================================
+def snapshot(net):
+    """Device-resident replacement of ``torch.save(net.state_dict(), pthname)`` (resnet50_main.py:212):
+    quantised layers are kept as packed codes (slq_store.Snapshot), nothing touches the file system."""
+    import slq_store
+    return slq_store.snapshot(net)
+
+
+def restore(net, snap):
+    """Replacement of ``net.load_state_dict(torch.load(pthname))`` (resnet50_main.py:233-234)."""
+    import slq_store
+    return slq_store.restore(net, snap)
+
+
+def save_packed(net, path):
+    import slq_store
+    return slq_store.save_packed(net, path)
+
+
+def load_packed(path, net):
+    import slq_store
+    return slq_store.load_packed(path, net)
+
+
+# ==============================================================================================
+# delta-loss table generator (SURVEY.md 8f: N3)
+# ==============================================================================================
+_LAYER_DEPTHS = {"resnet18": [2, 2, 2, 2], "resnet34": [3, 4, 6, 3], "resnet50": [3, 4, 6, 3]}
+
+
+def quantized_convs(arch, net):
+    """[(layer number 1.., conv module)] in the order of the reference's tables (dataset/*_deltaloss.csv row 0;
+    resnet50_main.py:81-136: block = (lnum-1)//convs_per_block in flattened stage order)."""
+    cpb = _CONVS_PER_BLOCK[arch]
+    blocks = [b for stage in (net.layer1, net.layer2, net.layer3, net.layer4) for b in stage]
+    return [(i * cpb + j + 1, getattr(b, "conv%d" % (j + 1))) for i, b in enumerate(blocks) for j in range(cpb)]
+
+
+def make_deltaloss_table(arch, net, device, data_loader, bits=(8, 6, 4), layers=None, channels=None, shard=True):
+    """Regenerates the per-channel sensitivity table the reference ships as ``dataset/<arch>_deltaloss.csv``
+    but cannot rebuild (its generator is the dead helper ``evaluate_loss``, functions.py:45-82):
+    for every output channel c of every quantised conv layer and every bit-width b,
+        deltaloss[b][c] = loss(net with ONLY channel c fake-quantised to b bits from fp32) - loss(net).
+    One candidate = one row through the quantizer kernel + one pass over the loader; the row is restored
+    from a device copy afterwards.  Candidates are dealt round-robin over the torch.distributed ranks and
+    exchanged with ONE all_gather, like the semilayer sweep (22,656 x 3 candidates for ResNet-50).
+    layers: iterable of layer numbers (default all); channels: callable(lnum, Cout) -> iterable of channel
+    indices (default all).  Returns (lnums, cnums_1based, {bit: [deltaloss...]}) in table column order."""
+    dist, rank, world = _dist() if shard else (None, 0, 1)
+    net.to(device)
+    net.eval()
+    base = _evaluate(net, device, data_loader, want_probs=False)[1]
+    cols = []
+    for lnum, conv in quantized_convs(arch, net):
+        if layers is not None and lnum not in layers:
+            continue
+        chans = range(conv.out_channels) if channels is None else channels(lnum, conv.out_channels)
+        cols += [(lnum, conv, int(c)) for c in chans]
+    values = torch.zeros(len(cols) * len(bits), dtype=torch.float64)
+    flags = torch.zeros_like(values)
+    first_error = None
+    for ci, (lnum, conv, c) in enumerate(cols):
+        if ci % world != rank:
+            continue
+        w = conv.weight.data
+        keep = w[c].clone()
+        for bi, b in enumerate(bits):
+            try:
+                quantize_rows(w, [c], [b], write_back=True, want_codes=False)
+                values[ci * len(bits) + bi] = _evaluate(net, device, data_loader, want_probs=False)[1] - base
+            except Exception as e:
+                flags[ci * len(bits) + bi] = 1.0
+                first_error = first_error or e
+            finally:
+                w[c].copy_(keep)
+                resnet.note_weight_write(w)
+    if world > 1:
+        _gather_values(values, flags, dist, world)
+    if bool(flags.any()):
+        if first_error is not None:
+            raise first_error
+        raise RuntimeError("delta-loss table: %d candidates failed on another rank" % int(flags.sum()))
+    v = values.reshape(len(cols), len(bits)).numpy()
+    return [c[0] for c in cols], [c[2] + 1 for c in cols], {int(b): v[:, i].tolist() for i, b in enumerate(bits)}
+
+
+def write_deltaloss_csv(path, lnums, cnums, table, bits=(8, 6, 4)):
+    """Writes the table in the reference's layout (resnet50_main.py:59-79 reads it back): UTF-8 with BOM,
+    row 0 layer numbers, row 1 1-based channel numbers, then one row of delta-loss values per bit-width."""
+    import csv
+    with open(path, "w", encoding="utf-8-sig", newline="") as f:
+        wr = csv.writer(f)
+        wr.writerow(lnums)
+        wr.writerow(cnums)
+        for b in bits:
+            wr.writerow([repr(float(x)) for x in table[int(b)]])
 
 
 def make_quantizedlists(semilayers, orders):

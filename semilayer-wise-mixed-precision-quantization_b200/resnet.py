@@ -157,6 +157,7 @@ class ResNet(nn.Module):
         state = dict(self.__dict__)
         state["_slq_engines"] = {}
         state["_slq_dirty"] = True
+        state.pop("_slq_donor", None)
         return state
 
     def __setstate__(self, state):
@@ -172,10 +173,19 @@ class ResNet(nn.Module):
         if eng is None:
             old = next(iter(self._slq_engines.values()), None)
             eng = slq_engine.Engine(self, x.shape[0], x.shape[2], x.shape[3], x.device, **kw)
+            donor = getattr(self, "_slq_donor", None)
+            if old is None and donor is not None:
+                old = next((e for e in getattr(donor, "_slq_engines", {}).values()), None)
             if old is not None and old.calibrated and len(old.act) == len(eng.act) and old.calib_hw == (x.shape[2], x.shape[3]):
-                eng.adopt_scales(old)  # same network, same image size, other batch size: ranges carry over
+                eng.adopt_scales(old)  # same network, same image size (other batch size): ranges carry over
             self._slq_engines = {key: eng}  # one live shape at a time (activation buffers are large)
         return eng
+
+    def slq_share_calibration(self, other):
+        """Use ``other``'s activation scales (same architecture, same image size) instead of calibrating on
+        the first batch: the un-quantised model and the candidates of a sweep must be compared under the SAME
+        activation quantisation, or re-calibration noise lands on top of the effect being measured."""
+        self._slq_donor = other
 
     def slq_calibrate(self, batches, headroom=1.0):
         """Explicit calibration of the static per-tensor activation scales (the reference never quantises

@@ -54,22 +54,23 @@ def packed_offsets(bits_host, K):
 
 def classify_weights(weights, stream=None):
     """slq_classify_rows over a list of fp32 [Cout, K] device tensors, one host sync in total.
-    Returns per tensor (bits_dev, z_dev, s_dev, bits_host)."""
+    Returns per tensor (bits_dev, z_dev, s_dev, bits_host, all_rows_exact)."""
     lib = L.lib()
     stream = L.current_stream() if stream is None else stream
     metas = []
     for w in weights:
         rows, K = w.shape[0], w[0].numel()
-        bit = torch.empty(rows, dtype=torch.int32, device=w.device)
+        meta = torch.empty((2, rows), dtype=torch.int32, device=w.device)  # bit | exact
         z = torch.empty(rows, dtype=torch.int32, device=w.device)
         s = torch.empty(rows, dtype=torch.float32, device=w.device)
-        L.check(lib.slq_classify_rows(w.data_ptr(), rows, K, bit.data_ptr(), z.data_ptr(), s.data_ptr(), stream))
-        metas.append((bit, z, s))
-    all_bits = torch.cat([m[0] for m in metas]).cpu().numpy()  # the one sync
+        L.check(lib.slq_classify_rows(w.data_ptr(), rows, K, meta[0].data_ptr(), z.data_ptr(), s.data_ptr(),
+                                      meta[1].data_ptr(), stream))
+        metas.append((meta, z, s))
+    all_meta = torch.cat([m[0] for m in metas], dim=1).cpu().numpy()  # the one sync
     out, pos = [], 0
-    for (bit, z, s) in metas:
-        n = bit.numel()
-        out.append((bit, z, s, all_bits[pos:pos + n]))
+    for (meta, z, s) in metas:
+        n = meta.shape[1]
+        out.append((meta[0], z, s, all_meta[0, pos:pos + n], bool(all_meta[1, pos:pos + n].all())))
         pos += n
     return out
 
@@ -255,9 +256,9 @@ class Engine:
             if todo:
                 ws = [op.conv.weight.detach().to(torch.float32).reshape(op.Cout, -1).contiguous() for op, _, _ in todo]
                 metas = classify_weights(ws, stream)
-                for (op, wsig, bsig), w2d, (bit, z, s, bits_host) in zip(todo, ws, metas):
+                for (op, wsig, bsig), w2d, (bit, z, s, bits_host, exact) in zip(todo, ws, metas):
                     op.packed = encode_weight(w2d, bit, z, s, bits_host, stream)
-                    op.bits_host = bits_host
+                    op.bits_host, op.packed_exact = bits_host, exact
                     w16 = 1 if int(bits_host.max()) > 8 else 0
                     var = op.variants.get(w16)
                     if var is None:  # first time this layer is seen in this mode: buffers + handle, kept for good

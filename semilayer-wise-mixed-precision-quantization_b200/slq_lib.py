@@ -41,7 +41,12 @@ SIGNATURES = {
     "slq_packed_row_bytes": (_i64, [_i64, _i32]),
     "slq_quantize_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "slq_quantize_rows_host": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "slq_classify_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "slq_quantize_jobs": (ctypes.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "slq_decode_rows": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _vp]),
+    "slq_eval_tail": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "slq_kl_rows": (ctypes.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "slq_probe_i8_peak": (ctypes.c_int, [_i32, ctypes.POINTER(_i64), _vp]),
+    "slq_classify_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "slq_encode_rows": (ctypes.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "slq_gemm_weight_rows": (_i64, [ctypes.POINTER(ConvDesc)]),
     "slq_build_gemm_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),

@@ -85,7 +85,7 @@ class ConvCase:
         self.x = rng.integers(0, 256, (N, H, H, cin), dtype=np.uint8)
         self.xd = torch.from_numpy(self.x).to(device)
         wd = torch.from_numpy(self.w.reshape(cout, -1)).to(device)
-        (bit, z, s, bits_host), = slq_engine.classify_weights([wd])
+        (bit, z, s, bits_host, _exact), = slq_engine.classify_weights([wd])
         self.bits_dev, self.z_dev, self.s_dev, self.bits_host = bit, z, s, bits_host
         self.packed = slq_engine.encode_weight(wd, bit, z, s, bits_host)
         self.desc = L.ConvDesc(N, H, H, cin, cout, k, k, stride, self.pad, self.w16, impl, a_mode)

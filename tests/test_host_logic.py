@@ -181,3 +181,41 @@ def test_packed_row_sizes_match_the_library():
     for K in (1, 3, 64, 65, 576, 1152, 4608):
         want = [lib.slq_packed_row_bytes(K, int(b)) for b in bits]
         assert functions.packed_row_bytes(K, bits).tolist() == want, K
+
+
+def test_packed_container_roundtrip():
+    """SLQPACK1 (slq_store.dumps / loads) is plain host logic: header, 64-byte aligned arrays, dtypes."""
+    import slq_store
+    g = torch.Generator().manual_seed(0)
+    packed = slq_store.Entry("layer1.0.conv1.weight", "packed", (4, 2, 3, 3), dict(
+        bits=torch.tensor([8, 4, 4, 2], dtype=torch.int32), z=torch.tensor([-120, -7, -8, -1], dtype=torch.int32),
+        s=torch.rand(4, generator=g), offsets=torch.tensor([0, 32, 48, 64], dtype=torch.int64),
+        blob=torch.randint(0, 256, (80,), generator=g, dtype=torch.uint8)), K=18)
+    dense = slq_store.Entry("bn1.running_var", "dense", (5,), dict(data=torch.rand(5, generator=g)))
+    count = slq_store.Entry("bn1.num_batches_tracked", "dense", (), dict(data=torch.tensor(7)))
+    raw = slq_store.dumps(slq_store.Snapshot([packed, dense, count], arch="BasicBlock"))
+    assert raw[:8] == b"SLQPACK1"
+    back = slq_store.loads(raw)
+    assert back.arch == "BasicBlock" and [e.name for e in back.entries] == [packed.name, dense.name, count.name]
+    for a, b in zip(back.entries, (packed, dense, count)):
+        assert a.kind == b.kind and a.shape == b.shape and a.K == b.K
+        for k in b.arrays:
+            assert a.arrays[k].dtype == b.arrays[k].dtype and torch.equal(a.arrays[k], b.arrays[k])
+    with pytest.raises(ValueError):
+        slq_store.loads(b"NOTAPACK" + raw[8:])
+
+
+def test_evaluate_cpu_route_is_the_reference_sequence():
+    """Host tensors take the stock-torch route of functions._evaluate: identical to the reference's loop."""
+    import functions
+    g = torch.Generator().manual_seed(1)
+    loader = [(torch.randn(5, 10, generator=g), torch.randint(0, 10, (5,), generator=g)) for _ in range(3)]
+    net = torch.nn.Identity()
+    acc, loss, outs = functions.evaluate_acc_loss_softmax(net, "cpu", loader)
+    crit = torch.nn.CrossEntropyLoss()
+    want_loss = (sum(crit(x, y) for x, y in loader) / 3).item()
+    want_acc = (torch.cat([x.max(1)[1] for x, _ in loader]) == torch.cat([y for _, y in loader])).float().mean().item()
+    assert loss == want_loss and abs(acc - want_acc) < 1e-7
+    assert all(torch.equal(o, torch.softmax(x, 1)) for o, (x, _y) in zip(outs, loader))
+    _, _, outs2, kl = functions._evaluate(net, "cpu", [(x * 1.1, y) for x, y in loader], ref_outputs=outs)
+    assert abs(kl - functions.KLdiv(outs, outs2)) < 1e-9

@@ -158,10 +158,15 @@ def test_classify_then_encode_reproduces_quantizer_codes():
         w = torch.from_numpy((rng.standard_normal((96, K)) * 0.05).astype(np.float32)).cuda()
         bits = np.array([8, 4, 6, 2] * 16, np.int32)
         pr = functions.quantize_rows(w, np.arange(64), bits, div_mode=L.DIV_TRUE)
-        (bit, z, s, bh), = slq_engine.classify_weights([w])
+        (bit, z, s, bh, exact), = slq_engine.classify_weights([w])
         assert np.array_equal(bh[:64], bits)
-        assert (bh[64:] == 16).all()
+        assert (bh[64:] == 16).all() and not exact   # untouched fp32 rows have no exact <= 8-bit grid
         assert np.array_equal(z.cpu().numpy()[:64], pr.z.cpu().numpy())
+        # the refined scale IS the scale the rows were quantised with (bit for bit), so that
+        # slq_decode_rows restores them exactly
+        assert np.array_equal(s.cpu().numpy()[:64].view(np.uint32), pr.s32.cpu().numpy().view(np.uint32))
+        (_b, _z, _s, _bh, exact64), = slq_engine.classify_weights([w[:64].contiguous()])
+        assert exact64
         packed = slq_engine.encode_weight(w, bit, z, s, bh)
         blob = packed.blob.cpu().numpy()
         offs = packed.offsets.cpu().numpy()
@@ -174,3 +179,10 @@ def test_classify_then_encode_reproduces_quantizer_codes():
             ob, oc, oz, os_ = so.encode_row(wh[j])
             assert ob == bh[j] and oz == int(z[j]) and np.array_equal(oc, codes)
             assert np.float32(os_) == s.cpu().numpy()[j]
+        # decode: packed rows -> fp32, bit-identical to the fake-quantised rows
+        back = torch.empty_like(w)
+        L.check(L.lib().slq_decode_rows(packed.blob.data_ptr(), packed.offsets.data_ptr(), packed.bits.data_ptr(),
+                                        packed.z.data_ptr(), packed.s.data_ptr(), 96, K, back.data_ptr(),
+                                        L.current_stream()))
+        assert np.array_equal(back.cpu().numpy()[:64].view(np.uint32), wh[:64].view(np.uint32))
+        assert np.allclose(back.cpu().numpy()[64:], wh[64:], atol=float(np.abs(wh[64:]).max()) / 60000)
