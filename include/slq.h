@@ -188,6 +188,13 @@ typedef struct slq_epilogue {
   int32_t *out_S;          /* SLQ_OUT_ACC only: [M] window sums, may be NULL                       */
   int32_t out_mode;
   int32_t relu;
+  /* Per-pixel channel sums ("rowsum") of u8 activations: the zero-point term z[oc] * S[m] needs the window sum
+   * S[m] of the INPUT; the tcgen05 kernel gathers it from in_rowsum (<= 9 taps) instead of spending tensor
+   * work on a row of ones.  Every producer of a u8 activation fills the side tensor of its output:       */
+  const uint32_t *in_rowsum; /* [N*H*W] sum over Cin of the input pixel (required by SLQ_IMPL_UMMA;
+                                the SIMT checker computes S itself and ignores it)                       */
+  uint32_t *out_rowsum;      /* [M] SLQ_OUT_U8 only, may be NULL: += sum over Cout of the u8 output pixel
+                                (atomic adds from the n-tiles: the caller zeroes it before the launch)   */
 } slq_epilogue;
 
 /* Debug timeline: when buf != NULL, CTA 0 of every later slq_conv_launch logs (event+1, index, SM clock)
@@ -195,6 +202,10 @@ typedef struct slq_epilogue {
  * each).  Events: 0/1 A load issue begin/end, 2/3 B load issue begin/end, 4 MMA saw K block, 5/6
  * epilogue tile begin/end.  NULL switches tracing off.  Not for production use.                    */
 SLQ_API int slq_debug_set_trace(int64_t *buf, int32_t capacity_events);
+
+/* cudaMemsetAsync(p, 0, bytes) on `stream`: zeroes the rowsum side tensors at the start of a forward pass
+ * (captured as a memset node when the forward is recorded into a CUDA graph).                        */
+SLQ_API int slq_zero_async(void *p, int64_t bytes, void *stream);
 
 /* y[m, oc] = (acc[m,oc] + z[oc] * S[m]) * wscale[oc] * act_scales[in_id] + bias[oc]
  *            (+ res[m,oc] * act_scales[res_id]) ; ReLU ; u8 = clamp(rint(y / act_scales[out_id])) */
@@ -207,10 +218,11 @@ SLQ_API int slq_conv_launch(slq_conv *c, const slq_epilogue *e, void *stream);
 /* Stem: resnet.py:206-209  conv1 7x7 s2 p3 (3->64, fp32 weights) + bn1 + relu + maxpool 3x3 s2 p1.
  * x fp32 NCHW [N,3,H,W] -> out NHWC [N,Hp,Wp,64], Hp = ((H+1)/2+1)/2 (u8 via act_scales[out_id], or
  * fp32 when out_mode == SLQ_OUT_F32).  `scratch` holds the pre-pool activations:
- * N*Hc*Wc*64 floats with Hc = (H+1)/2.                                                          */
+ * N*Hc*Wc*64 floats with Hc = (H+1)/2.  out_rowsum (SLQ_OUT_U8, may be NULL): [N*Hp*Wp] += channel sum of
+ * every output pixel (see slq_epilogue.in_rowsum; zeroed by the caller).                          */
 SLQ_API int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W, const float *w,
                      const float *bn_a, const float *bn_b, const float *act_scales, int32_t out_id,
-                     float *scratch, void *out, int32_t out_mode, void *stream);
+                     float *scratch, void *out, int32_t out_mode, uint32_t *out_rowsum, void *stream);
 
 /* The same stem on the tensor cores (the product path; slq_stem_forward above is the exact-fp32
  * CUDA-core version kept as on-device checker and for W > 256).  Operands pass through tcgen05 as
@@ -227,7 +239,7 @@ SLQ_API void slq_stem_destroy(slq_stem *s);
 SLQ_API int slq_stem_set_weights(slq_stem *s, const float *w, void *stream);
 SLQ_API int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, const float *bn_b,
                             const float *act_scales, int32_t out_id, void *out, int32_t out_mode,
-                            float *f32_scratch, void *stream);
+                            float *f32_scratch, uint32_t *out_rowsum, void *stream);
 /* The same launch for the other element types a loader may hand over (the data format on the host side
  * of the path, imagenet.py:14-40): SLQ_IN_F16 = the fp32 image already rounded to fp16 (the stem rounds
  * its operands to fp16 anyway, so the logits are bit-identical to the fp32 call); SLQ_IN_U8 = raw pixels,
@@ -238,7 +250,7 @@ SLQ_API int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, cons
 #define SLQ_IN_U8 2
 SLQ_API int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, const float *norm,
                                const float *bn_a, const float *bn_b, const float *act_scales, int32_t out_id,
-                               void *out, int32_t out_mode, float *f32_scratch, void *stream);
+                               void *out, int32_t out_mode, float *f32_scratch, uint32_t *out_rowsum, void *stream);
 
 /* Tail: resnet.py:216-218  adaptive_avg_pool2d((1,1)) + flatten + fc (fp32 weights + bias).
  * x u8 NHWC [N, HW, C] -> logits fp32 [N, O]; pooled is scratch [N, C] fp32.                     */

@@ -7,8 +7,15 @@
 //   A = NHWC u8 activations, gathered by TMA: im2col-mode tensor map for 3x3 / strided layers
 //       (zero padding and the (r,s) filter offsets are resolved by the TMA unit), tiled map for
 //       1x1 stride-1 layers;  B = GEMM-ready weight codes [rows, K], K ordered (r, s, c).
-//   One extra "ones" B row per tile makes the tensor core also produce the window sum
-//   S[m] = sum_k A[m, k] that the zero-point correction z[oc]*S[m] needs.
+//   The zero-point correction z[oc]*S[m] needs the window sum S[m] = sum_k A[m, k]: every
+//   producer of a u8 activation also accumulates its per-pixel channel sums into a side tensor
+//   (rowsum, 4 bytes per pixel: one DP4A per four outputs + one RED per thread and tile), and the consumer's
+//   epilogue gathers the <= 9 taps of its window from it.  (Round 1 appended a row of ones to every B tile
+//   instead: N = 144, 12.5 % more tensor work and no room for the N = 256 tiles below.)
+//   K-heavy layers (weights streamed, Cout % 256 == 0) run 256-channel tiles: UMMA N = 256 is the shape at
+//   which one tcgen05.mma occupies the tensor pipe for as long as a warp needs to issue the next one
+//   (128 cycles, tools/issue_bench.cu), and a K block then moves 48 KB per 512 tensor cycles instead of
+//   32 KB per 288 -- the L2 -> SM path (~75 B/clk/SM through TMA) was what capped the 128-channel tiles.
 //
 // Persistent, warp-specialised CTA (640 threads, 1 CTA/SM):
 //   warps 0, 2  TMA producers: pipeline step c (one smem stage = 1-4 K blocks of A, plus the K block's B tile
@@ -52,34 +59,40 @@ struct SmemPlan {
   int stage_bytes;   // stride between stages
   int group;         // K blocks per stage (1 when B is streamed)
   int a_bytes;       // kTileM * SWZ
-  int b_tile_bytes;  // (bn_cols + 16) * SWZ
+  int b_tile_bytes;  // bn_cols * SWZ
   int b_resident;    // 1: B tiles at b_off + kb * b_tile_bytes ; 0: inside each stage after A
   int mma_warps;     // 2: warps 1 and 3 issue MMAs (1: warp 1 only; experiments)
   int b_off;
   int res_bufs;      // depth of the residual (block identity) prefetch ring, 0 without residual
-  int out_bufs;      // output staging tiles: one per epilogue team, or ONE shared by both (streamed weights)
+  int out_bufs;      // output staging tiles: one per epilogue team, ONE shared by both (streamed weights), or
+                     // NONE (256-channel tiles store straight from registers)
   int out_off, res_off, prm_off, bar_off;
   int total;         // dynamic smem bytes to request (including 1024 B of alignment slack)
 };
 
 constexpr int kMaxResBufs = 4;
+constexpr int kPrmBytes = 2 * 3 * 256 * 4;  // per team: A[256] | Z[256] | B[256] floats
 constexpr int kMaxGroup = 4;
 
 inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
   SmemPlan p{};
   p.a_bytes = kTileM * swz;
-  p.b_tile_bytes = (g.bn_cols + 16) * swz;
+  p.b_tile_bytes = g.bn_cols * swz;
   const int num_kb = g.Ktot / swz;
   const long long b_all = (long long)num_kb * p.b_tile_bytes;
-  static const int force_group = getenv("SLQ_GROUP") ? atoi(getenv("SLQ_GROUP")) : 0;     // experiments only
+#if SLQ_DEBUG_TRACE  // experiment knobs exist only in the debug build of the library
+  static const int force_group = getenv("SLQ_GROUP") ? atoi(getenv("SLQ_GROUP")) : 0;
   static const int force_mma = getenv("SLQ_MMA_WARPS") ? atoi(getenv("SLQ_MMA_WARPS")) : 0;
+#else
+  constexpr int force_group = 0, force_mma = 0;
+#endif
   // EVEN depth: stage-sized step c goes to producer / MMA warp c & 1 and to stage c % stages, so with an
   // even depth every stage barrier is always waited on by the same warp (an mbarrier wait only names a
   // phase parity; a warp that saw every other phase of a barrier could not tell them apart)
   p.stages = 0;
-  for (int rb = has_res ? kMaxResBufs : 0; p.stages == 0 && rb >= (has_res ? 2 : 0); rb -= 2) {
+  for (int rb = has_res ? kMaxResBufs : 0; g.bn_ch != 256 && p.stages == 0 && rb >= (has_res ? 2 : 0); rb -= 2) {
     // out staging (2), residual ring, prm, barriers, alignment slack
-    const int fixed = (2 + rb) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
+    const int fixed = (2 + rb) * kOutTileBytes + kPrmBytes + 512 + 1024;
     const long long room = (long long)kSmemLimit - fixed - b_all;  // for A stages when B is resident
     for (int grp = std::min(kMaxGroup, num_kb); grp >= 1; --grp) {
       if (num_kb % grp != 0 || (force_group && grp > force_group)) continue;
@@ -96,8 +109,8 @@ inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
     // time, and the {A, B} ring is what runs short (2 -> 4 stages: 54 -> 37 us on the 3x3 256 layer), so
     // the two teams share ONE staging tile and the 16 KB go to the ring (6 stages without residual)
     p.res_bufs = has_res ? kMaxResBufs : 0;
-    p.out_bufs = 1;
-    const int fixed = (p.out_bufs + p.res_bufs) * kOutTileBytes + 2 * 128 * 16 + 512 + 1024;
+    p.out_bufs = g.bn_ch == 256 ? 0 : 1;
+    const int fixed = (p.out_bufs + p.res_bufs) * kOutTileBytes + kPrmBytes + 512 + 1024;
     p.b_resident = 0;
     p.group = 1;
     p.stage_bytes = p.a_bytes + p.b_tile_bytes;
@@ -108,7 +121,7 @@ inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
   p.out_off = p.b_off + (p.b_resident ? (int)b_all : 0);
   p.res_off = p.out_off + p.out_bufs * kOutTileBytes;
   p.prm_off = p.res_off + p.res_bufs * kOutTileBytes;
-  p.bar_off = p.prm_off + 2 * 128 * 16;
+  p.bar_off = p.prm_off + kPrmBytes;
   p.total = 1024 + p.bar_off + 512;
   return p;
 }
@@ -135,6 +148,7 @@ struct KernelArgs {
   int tma_out;         // 1: u8/s8 output through the smem tile + TMA store
   int mma_warps_per_tile;  // MMA warps that touch one tile: 2, or 1 when a tile is a single K block / tile_alt
   int tile_alt;            // the two MMA warps alternate whole tiles instead of pipeline steps
+  int acc_bufs, acc_stride;  // TMEM accumulator ring: 3 x 160 columns (N <= 128), 2 x 256 (N = 256)
   long long m_tiles;
   long long *trace;    // debug: CTA 0 logs (event, index, clock) triples here (slq_debug_set_trace)
   int trace_cap;
@@ -197,9 +211,9 @@ struct TileWalk {  // everything fits 32 bits (M <= 2^31): no 64-bit divisions o
   }
 };
 
-constexpr int kAccBufs = 3;      // accumulator ring in TMEM: tile i -> buffer i % 3
-constexpr int kTileBars = 6;     // per-tile barrier sets: tile i -> set i % 6 (see the barrier table)
-constexpr int kAccStride = 160;  // TMEM columns between accumulator buffers (>= largest UMMA N = 144)
+// accumulator ring in TMEM: tile i -> buffer i % acc_bufs (KernelArgs: 3 buffers 160 columns apart, or 2 x 256
+// for the 256-channel tiles)
+constexpr int kTileBars = 6;     // per-tile barrier sets: tile i -> set i % 6 (a multiple of acc_bufs and of the 2 teams)
 constexpr int kTmemCols = 512;
 
 // byte offset of 16-byte chunk c of row r inside a staging tile whose rows are bn_ch (64|128) bytes,
@@ -245,7 +259,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const ConvGeom &g = a.g;
   const EpiDev &e = a.e;
   const int bn_cols = g.bn_cols;
-  const int umma_n = bn_cols + 16;
+  const int umma_n = bn_cols;
   const bool has_res = RES == kResDyn ? (e.res != nullptr) : (RES != kResNone);
   const TileWalk walk(a);
 
@@ -283,20 +297,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  // constant "ones" row group behind the TMA-written B rows of every B tile:
-  // row bn_cols = 0x01.., rows bn_cols+1 .. +15 = 0  (identical bytes are swizzle-invariant)
-  {
-    const int b_tiles = sp.b_resident ? a.num_kb : sp.stages;
-    const int b_stride = sp.b_resident ? sp.b_tile_bytes : sp.stage_bytes;
-    const int b_first = sp.b_resident ? sp.b_off : sp.a_bytes;
-    for (int i = threadIdx.x; i < b_tiles * 16 * (SWZ / 16); i += blockDim.x) {
-      const int t = i / (16 * (SWZ / 16));
-      const int rem = i % (16 * (SWZ / 16));
-      const int row = rem / (SWZ / 16), chunk = rem % (SWZ / 16);
-      uint4 v = row == 0 ? make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u) : make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4 *>(smem + b_first + t * b_stride + (bn_cols + row) * SWZ + chunk * 16) = v;
-    }
   }
   fence_proxy_async_smem();
   tc_fence_before();
@@ -476,16 +476,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int c = c0; c < items;) {
       if (i != cur_i) {  // this warp's first step of tile i
         cur_i = i;
-        acc = i % kAccBufs;
+        acc = i % a.acc_bufs;
         tb = i % kTileBars;
         if (gi == 0) {  // the epilogue of tile i - 3 has drained this accumulator
-          if (i >= kAccBufs) mbar_wait_stat(tempty_bar((i - kAccBufs) % kTileBars), (uint32_t)(((i - kAccBufs) / kTileBars) & 1), wacc, stats);
+          if (i >= a.acc_bufs) mbar_wait_stat(tempty_bar((i - a.acc_bufs) % kTileBars), (uint32_t)(((i - a.acc_bufs) / kTileBars) & 1), wacc, stats);
         } else {        // the overwriting MMAs of this tile have completed
           mbar_wait_stat(tstart_bar(tb), (uint32_t)((i / kTileBars) & 1), wacc, stats);
         }
         tc_fence_after();
       }
-      const uint32_t tmem_d = tmem_u + acc * kAccStride;
+      const uint32_t tmem_d = tmem_u + acc * a.acc_stride;
       const uint32_t a_lo = a_lo_first + (uint32_t)stage * stage16;
       const uint32_t b_lo = resident ? b_lo_first + (uint32_t)(gi * grp) * btile16 : a_lo + a16;
       const bool last_mine = tile_alt ? gi + 1 == ngrp : gi + nmw >= ngrp;  // this warp's last step of the tile
@@ -533,8 +533,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // A warp-wide broadcast LDS.128 costs the LSU four wavefronts whatever it delivers (measured: the LSU
     // data pipe was the busiest unit of the epilogue with one {A,Z,B,pad} load per output), so one load
     // fetches the same constant of FOUR channels: 3 wavefronts per channel instead of 4, 0.75 loads per output.
-    float *prm = reinterpret_cast<float *>(smem + sp.prm_off) + team * 512;
-    const uint32_t prm_s = smem_base + sp.prm_off + team * 128 * 16;
+    float *prm = reinterpret_cast<float *>(smem + sp.prm_off) + team * 768;
+    const uint32_t prm_s = smem_base + sp.prm_off + team * 3072;
     const bool shared_stg = sp.out_bufs == 1;  // both teams stage through one tile (stfree hand-off below)
     const uint32_t stg = smem_base + sp.out_off + (shared_stg ? 0 : team) * kOutTileBytes;
     float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
@@ -553,7 +553,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int it = team; it < walk.count; it += 2) {
       int m_tile, n_tile;
       walk.at(it, m_tile, n_tile);
-      const int acc = it % kAccBufs, tb = it % kTileBars;
+      const int acc = it % a.acc_bufs, tb = it % kTileBars;
       const uint32_t ph = (uint32_t)((it / kTileBars) & 1);
       // staging tile free again? (the previous TMA store of this team has read it)
       if (a.tma_out && et == 0) tma_store_wait_read();
@@ -563,10 +563,37 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int oc = n_tile * g.bn_ch + et;
           ChanParam p = {0.f, 0.f, 0.f, 0.f};
           if (oc < g.Cout) p = make_chan_param(e.wscale[oc], e.zf[oc], e.bias[oc], s_in, inv_out, kQuant);
-          prm[et] = p.wsc; prm[128 + et] = p.zw; prm[256 + et] = p.bias;
+          prm[et] = p.wsc; prm[256 + et] = p.zw; prm[512 + et] = p.bias;
         }
         last_n_tile = n_tile;
         named_bar_sync(1 + team, kTeam);
+      }
+      // window sum of the INPUT activation for this thread's output pixel, from the per-pixel channel sums the
+      // producing kernel accumulated (<= 9 loads, issued before the wait for the accumulator)
+      const long long m = (long long)m_tile * kTileM + row;
+      const bool valid = m < g.M;
+      uint32_t S_raw = 0;
+      if (valid) {
+        const int hw = g.Ho * g.Wo;
+        const int n_img = (int)(m / hw);
+        const int rem = (int)(m - (long long)n_img * hw);
+        const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
+        const uint32_t *rs = e.in_rowsum + (long long)n_img * g.H * g.W;
+        if (g.kh == 1) {
+          S_raw = __ldg(rs + (ho * g.stride) * g.W + wo * g.stride);
+        } else {
+          const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const int hi = h0 + r;
+            if (hi < 0 || hi >= g.H) continue;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+              const int wi = w0 + q;
+              if (wi >= 0 && wi < g.W) S_raw += __ldg(rs + hi * g.W + wi);
+            }
+          }
+        }
       }
       mbar_wait_stat(tfull_bar(tb), ph, wepi, kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0);
       tc_fence_after();
@@ -574,12 +601,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int rbuf = has_res ? (int)(it % sp.res_bufs) : 0;
       const uint32_t rsb = smem_base + sp.res_off + rbuf * kOutTileBytes;
       if (has_res) mbar_wait(rfull_bar(rbuf), (uint32_t)((it / sp.res_bufs) & 1));
-      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kAccStride;
-      const long long m = (long long)m_tile * kTileM + row;
-      const bool valid = m < g.M;
-      const uint32_t S_raw = tmem_ld1(trow + bn_cols);
-      tmem_ld_wait();
-      const float Sf = (float)(int)S_raw;
+      const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * a.acc_stride;
+      const float Sf = (float)S_raw;  // <= 9 * 2048 * 255 < 2^24: exact
+      uint32_t rsum = 0;              // channel sum of this thread's u8 outputs of the tile
       if (OUT == SLQ_OUT_ACC && e.out_S && valid && n_tile == 0 && half == 0) e.out_S[m] = (int)S_raw;
       for (int u = u0; u < u1; ++u) {
         uint32_t lo[CW], hi[CW];
@@ -611,22 +635,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool store_ok = valid && cb < g.Cout;
         float4 *of = reinterpret_cast<float4 *>(reinterpret_cast<float *>(e.out) + m * g.Cout + cb);
         uint32_t pk[CW / 4];
+        const float2 S2 = make_float2(Sf, Sf), R2 = make_float2(s_res, s_res);
 #pragma unroll
         for (int q4 = 0; q4 < CW / 4; ++q4) {
           float v[4];
           const uint32_t pofs = prm_s + (uint32_t)(u * CW + 4 * q4) * 4;  // warp-wide broadcast loads
-          const uint4 pa = lds128(pofs), pz = lds128(pofs + 512), pb = lds128(pofs + 1024);
+          const uint4 pa = lds128(pofs), pz = lds128(pofs + 1024), pb = lds128(pofs + 2048);
           const uint32_t pav[4] = {pa.x, pa.y, pa.z, pa.w}, pzv[4] = {pz.x, pz.y, pz.z, pz.w}, pbv[4] = {pb.x, pb.y, pb.z, pb.w};
+          // two channels per FFMA2 (packed fp32 pairs): the arithmetic of epi_value / epi_add_res, component-wise
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
+          for (int b = 0; b < 4; b += 2) {
             const int j = 4 * q4 + b;
-            ChanParam p;
-            p.wsc = __uint_as_float(pav[b]); p.zw = __uint_as_float(pzv[b]); p.bias = __uint_as_float(pbv[b]);
-            v[b] = epi_value<W16>((int)lo[j], W16 ? (int)hi[j] : 0, Sf, p);
+            float2 accf = make_float2((float)(int)lo[j], (float)(int)lo[j + 1]);
+            if (W16) accf = ffma2(make_float2((float)(int)hi[j], (float)(int)hi[j + 1]), make_float2(256.0f, 256.0f), accf);
+            const float2 c2 = ffma2(S2, make_float2(__uint_as_float(pzv[b]), __uint_as_float(pzv[b + 1])),
+                                    make_float2(__uint_as_float(pbv[b]), __uint_as_float(pbv[b + 1])));
+            float2 y = ffma2(accf, make_float2(__uint_as_float(pav[b]), __uint_as_float(pav[b + 1])), c2);
             if (has_res) {
-              const uint32_t byte = (rw[q4] >> (8 * b)) & 255u;
-              v[b] = epi_add_res(v[b], byte, res_signed, s_res);
+              const uint32_t b0 = (rw[q4] >> (8 * b)) & 255u, b1 = (rw[q4] >> (8 * b + 8)) & 255u;
+              const float2 r = res_signed ? make_float2((float)(int)(int8_t)b0, (float)(int)(int8_t)b1)
+                                          : make_float2((float)b0, (float)b1);
+              y = ffma2(r, R2, y);
             }
+            v[b] = y.x; v[b + 1] = y.y;
           }
           if (!kQuant) {
             if (e.relu) {
@@ -636,17 +667,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (store_ok) of[q4] = make_float4(v[0], v[1], v[2], v[3]);
           } else {
             pk[q4] = epi_pack4<OUT == SLQ_OUT_S8>(v[0], v[1], v[2], v[3]);
+            if (OUT == SLQ_OUT_U8) rsum = __dp4a(pk[q4], 0x01010101u, rsum);
           }
         }
         if (kQuant) {
-          // shared staging tile: the other team's store of the previous tile must have read it
-          if (shared_stg && u == u0 && it >= 1) mbar_wait(stfree_bar(team ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
+          if (a.tma_out) {
+            // shared staging tile: the other team's store of the previous tile must have read it
+            if (shared_stg && u == u0 && it >= 1) mbar_wait(stfree_bar(team ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
 #pragma unroll
-          for (int i = 0; i < CW / 16; ++i)
-            sts128(stg + stage_off(row, u * (CW / 16) + i, g.bn_ch),
-                   make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]));
+            for (int i = 0; i < CW / 16; ++i)
+              sts128(stg + stage_off(row, u * (CW / 16) + i, g.bn_ch),
+                     make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]));
+          } else if (store_ok) {
+            // 256-channel tiles: no staging tile (the smem goes to the {A, B} ring); a thread owns 128 contiguous
+            // bytes of its pixel, written as 16-byte stores that complete whole lines over the unit loop
+            uint4 *o = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(e.out) + m * g.Cout + cb);
+#pragma unroll
+            for (int i = 0; i < CW / 16; ++i) o[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
         }
       }
+      if (OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr && valid) atomicAdd(e.out_rowsum + m, rsum);
       tc_fence_before();
       if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
       mbar_arrive(tempty_bar(tb));  // kTeam arrivals release the accumulator buffer
@@ -749,12 +790,14 @@ static int build_tensor_maps(slq_conv *c) {
   const int swz = c->swizzle;
   const CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r;
-  {  // B: GEMM-ready weights [gemm_rows, Ktot] u8, box = SWZ bytes of K x bn_cols rows
-    cuuint64_t dims[2] = {(cuuint64_t)g.Ktot, (cuuint64_t)g.gemm_rows};
-    cuuint64_t strides[1] = {(cuuint64_t)g.Ktot};
-    cuuint32_t box[2] = {(cuuint32_t)swz, (cuuint32_t)g.bn_cols};
+  for (int wide = 0; wide <= (c->wide_ok ? 1 : 0); ++wide) {
+    // B: GEMM-ready weights [gemm_rows, Ktot] u8, box = SWZ bytes of K x bn_cols rows (one map per tiling)
+    const ConvGeom &gb = wide ? c->g_wide : c->g;
+    cuuint64_t dims[2] = {(cuuint64_t)gb.Ktot, (cuuint64_t)gb.gemm_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)gb.Ktot};
+    cuuint32_t box[2] = {(cuuint32_t)swz, (cuuint32_t)gb.bn_cols};
     cuuint32_t es[2] = {1, 1};
-    r = enc_tiled(&c->tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)c->wg, dims, strides, box, es,
+    r = enc_tiled(wide ? &c->tmB_wide : &c->tmB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, (void *)c->wg, dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -803,32 +846,38 @@ void debug_trace_buffer(long long **buf, int *cap) { *buf = g_trace; *cap = g_tr
 
 template <int SWZ, bool W16, int OUT, int RES>
 static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};  // function attributes are per device
+  const int dev = current_device();
+  if (dev >= kMaxDevices || !attr_done[dev]) {
     SLQ_CUDA(cudaFuncSetAttribute(conv_umma_kernel<SWZ, W16, OUT, RES>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    attr_done = true;
+    if (dev < kMaxDevices) attr_done[dev] = true;
   }
+  // K-heavy layers (weights streamed) without residual run 256-channel tiles
+  const bool wide = c->wide_ok && e.res == nullptr && !W16;
+  const ConvGeom &geom = wide ? c->g_wide : c->g;
   KernelArgs a;
-  a.g = c->g;
+  a.g = geom;
   a.e = e;
-  a.sp = make_plan(c->g, SWZ, e.res != nullptr);
-  const int grid = plan_grid(c->g, a.sp, sm_count());
+  a.sp = make_plan(geom, SWZ, e.res != nullptr);
+  a.acc_bufs = wide ? 2 : 3;
+  a.acc_stride = wide ? 256 : 160;
+  if (wide) tma_out = 0;  // straight from registers (no staging tile: the smem goes to the operand ring)
+  const int grid = plan_grid(geom, a.sp, sm_count());
   a.trace = g_trace;
   a.trace_cap = g_trace_cap;
   a.a_im2col = c->a_im2col;
-  a.chunks_per_tap = c->g.Cin / SWZ;
-  a.num_kb = c->g.kh * c->g.kw * a.chunks_per_tap;
+  a.chunks_per_tap = geom.Cin / SWZ;
+  a.num_kb = geom.kh * geom.kw * a.chunks_per_tap;
   a.num_grp = a.num_kb / a.sp.group;
-  static const bool no_tile_alt = getenv("SLQ_NO_TILE_ALT") != nullptr;  // experiments only
-  a.tile_alt = (!no_tile_alt && a.sp.mma_warps == 2 && a.num_grp >= 2 && a.sp.stages % (2 * a.num_grp) == 0) ? 1 : 0;
+  a.tile_alt = (a.sp.mma_warps == 2 && a.num_grp >= 2 && a.sp.stages % (2 * a.num_grp) == 0) ? 1 : 0;
   a.mma_warps_per_tile = (a.sp.mma_warps == 2 && a.num_grp >= 2 && !a.tile_alt) ? 2 : 1;
-  a.m_tiles = ceil_div(c->g.M, kTileM);
+  a.m_tiles = ceil_div(geom.M, kTileM);
   a.tma_out = tma_out;
   // Programmatic dependent launch: this grid's CTAs may start (barrier / TMEM set-up, resident weights)
   // on an SM as soon as the previous kernel's CTA there has exited; griddepcontrol.wait in the kernel
   // holds everything that touches activations until the previous grid has completed.
-  static const bool pdl = getenv("SLQ_NO_PDL") == nullptr;
+  const bool pdl = true;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kThreads);
@@ -839,7 +888,8 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  SLQ_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<SWZ, W16, OUT, RES>, c->tmA, c->tmB, c->tmO, c->tmR, a));
+  SLQ_CUDA(cudaLaunchKernelEx(&cfg, conv_umma_kernel<SWZ, W16, OUT, RES>, c->tmA, wide ? c->tmB_wide : c->tmB, c->tmO,
+                              c->tmR, a));
   return SLQ_OK;
 }
 
@@ -886,6 +936,10 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
   c->in = in;
   c->wg = wg;
   c->swizzle = (d->Cin % 128 == 0) ? 128 : 64;
+  c->g_wide = make_geom(*d, 1);
+  // wide tiles only where the 128-channel tiling has to stream its weights anyway (K-heavy layers)
+  c->wide_ok = (d->impl == SLQ_IMPL_UMMA && c->g_wide.bn_ch == 256 && c->swizzle == 128 &&
+                !make_plan(c->g, c->swizzle, false).b_resident) ? 1 : 0;
   c->out_ptr = nullptr;
   c->res_ptr = nullptr;
   const bool can_tile = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0;
@@ -941,6 +995,7 @@ extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream
                 "slq_conv_launch: out/res must be 16-byte aligned");
   EpiDev e;
   e.wscale = ep->wscale; e.zf = ep->zf; e.bias = ep->bias; e.act_scales = ep->act_scales;
+  e.in_rowsum = ep->in_rowsum; e.out_rowsum = ep->out_rowsum;
   e.res = ep->out_mode == SLQ_OUT_ACC ? nullptr : ep->res;
   e.out = ep->out; e.out_S = ep->out_S;
   e.in_id = ep->in_id; e.out_id = ep->out_id; e.res_id = ep->res_id;
@@ -948,6 +1003,7 @@ extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream
   e.Cout = c->g.Cout; e.w16 = c->g.w16; e.M = c->g.M;
   cudaStream_t st = (cudaStream_t)stream;
   if (c->desc.impl == SLQ_IMPL_SIMT) return launch_conv_simt(c->g, c->in, c->wg, e, st);
+  SLQ_CHECK_ARG(ep->in_rowsum != nullptr, "slq_conv_launch: in_rowsum (per-pixel channel sums of the input) is NULL");
   const int tma_out = (ep->out_mode == SLQ_OUT_U8 || ep->out_mode == SLQ_OUT_S8) ? 1 : 0;
   if (tma_out && c->out_ptr != ep->out) {  // (re)encode the store map for this output buffer
     int rc = encode_out_map(&c->tmO, ep->out, c->g, "out");

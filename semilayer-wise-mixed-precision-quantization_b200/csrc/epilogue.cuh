@@ -33,6 +33,8 @@ struct EpiDev {  // device-side view of slq_epilogue (+ layer constants)
   const uint8_t *res;
   void *out;
   int32_t *out_S;
+  const uint32_t *in_rowsum;  // [N*H*W] per-pixel channel sums of the INPUT activation (tcgen05 path)
+  uint32_t *out_rowsum;       // [M] per-pixel channel sums of the u8 OUTPUT, accumulated with atomics (or NULL)
   int in_id, out_id, res_id;
   int out_mode, relu, res_signed;
   int Cout, w16;
@@ -70,6 +72,19 @@ __device__ __forceinline__ float epi_value(int acc_lo, int acc_hi, float Sf, con
 __device__ __forceinline__ float epi_add_res(float y, uint32_t res_byte, bool res_signed, float s_res) {
   const float r = res_signed ? (float)(int)(int8_t)res_byte : (float)res_byte;
   return __fmaf_rn(r, s_res, y);
+}
+
+// two independent fused multiply-adds in ONE instruction (sm_100 FFMA2): d = a * b + c per component, each
+// rounded once, i.e. bit-identical to two __fmaf_rn calls
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  uint64_t ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
 }
 
 // y is already in units of the output scale (see the contract)

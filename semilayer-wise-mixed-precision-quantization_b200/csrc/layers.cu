@@ -204,7 +204,8 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float *__restrict_
 
 __global__ void __launch_bounds__(256) stem_pool_kernel(const float *__restrict__ y, int N, int Hc, int Wc,
                                                         int Hp, int Wp, const float *__restrict__ act_scales,
-                                                        int out_id, void *__restrict__ out, int out_mode) {
+                                                        int out_id, void *__restrict__ out, int out_mode,
+                                                        uint32_t *__restrict__ out_rowsum) {
   const long long total = (long long)N * Hp * Wp * 16;
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -229,13 +230,15 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float *__restrict_
     const uint32_t q = epi_quant_u8(__fmul_rn(m.x, inv)) | (epi_quant_u8(__fmul_rn(m.y, inv)) << 8) |
                        (epi_quant_u8(__fmul_rn(m.z, inv)) << 16) | (epi_quant_u8(__fmul_rn(m.w, inv)) << 24);
     *reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out) + pix * 64 + og * 4) = q;
+    if (out_rowsum) atomicAdd(out_rowsum + pix, __dp4a(q, 0x01010101u, 0u));
   }
 }
 
 int launch_stem_pool(const float *y, int N, int Hc, int Wc, int Hp, int Wp, const float *act_scales,
-                     int out_id, void *out, int out_mode, cudaStream_t st) {
+                     int out_id, void *out, int out_mode, uint32_t *out_rowsum, cudaStream_t st) {
   const long long total = (long long)N * Hp * Wp * 16;
-  stem_pool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode);
+  stem_pool_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(y, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode,
+                                                                  out_mode == SLQ_OUT_U8 ? out_rowsum : nullptr);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }
@@ -412,7 +415,7 @@ extern "C" int slq_build_gemm_weights(const slq_conv_desc *d, const uint8_t *cod
 extern "C" int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W, const float *w,
                                 const float *bn_a, const float *bn_b, const float *act_scales,
                                 int32_t out_id, float *scratch, void *out, int32_t out_mode,
-                                void *stream) {
+                                uint32_t *out_rowsum, void *stream) {
   SLQ_CHECK_ARG(x && w && bn_a && bn_b && scratch && out, "slq_stem_forward: null pointer argument");
   SLQ_CHECK_ARG(N > 0 && H >= 7 && W >= 7, "slq_stem_forward: bad shape");
   SLQ_CHECK_ARG(out_mode == SLQ_OUT_U8 || out_mode == SLQ_OUT_F32, "slq_stem_forward: out_mode %d", out_mode);
@@ -423,7 +426,7 @@ extern "C" int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W,
   dim3 grid((unsigned)ceil_div(Wc, kStemTile), (unsigned)ceil_div(Hc, kStemTile), (unsigned)N);
   stem_conv_kernel<<<grid, 256, 0, st>>>(x, N, H, W, Hc, Wc, w, bn_a, bn_b, scratch);
   SLQ_LAUNCH_CHECK();
-  return launch_stem_pool(scratch, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode, st);
+  return launch_stem_pool(scratch, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode, out_rowsum, st);
 }
 
 extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C,
@@ -464,5 +467,12 @@ extern "C" int slq_quantize_act(const float *y, int64_t n, const float *act_scal
   const int blocks = (int)std::min<int64_t>(ceil_div(n / 4 + 1, 256), (int64_t)sm_count() * 8);
   quantize_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, n, act_scales, id, is_signed, out);
   SLQ_LAUNCH_CHECK();
+  return SLQ_OK;
+}
+
+extern "C" int slq_zero_async(void *p, int64_t bytes, void *stream) {
+  SLQ_CHECK_ARG(p != nullptr && bytes >= 0, "slq_zero_async: bad argument");
+  if (bytes == 0) return SLQ_OK;
+  SLQ_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
   return SLQ_OK;
 }

@@ -19,12 +19,11 @@ __global__ void __launch_bounds__(128, 1) probe_i8_kernel(int iters) {
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (base - smem_u32(smem_raw));
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(8) uint64_t bars[2];
+  __shared__ __align__(8) uint64_t bars[2][4];
   const int w = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < (kProbeSmem - 1024) / 4; i += blockDim.x) reinterpret_cast<uint32_t *>(smem)[i] = 0x01010101u;
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&bars[0]), 1);
-    mbar_init(smem_u32(&bars[1]), 1);
+    for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i >> 2][i & 3]), 1);
     fence_barrier_init();
   }
   if (w == 3) {
@@ -37,28 +36,30 @@ __global__ void __launch_bounds__(128, 1) probe_i8_kernel(int iters) {
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   if (w < 2) {
-    const uint32_t bar = smem_u32(&bars[w]);
+    const uint32_t bar0 = smem_u32(&bars[w][0]);
     const uint32_t idesc = (2u << 4) | ((uint32_t)(kProbeN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint64_t dflags = make_smem_desc<128>(0);
     const uint32_t acc = tmem + (uint32_t)w * 256u;
     const uint32_t lo = (((base + (uint32_t)w * (16384 + kProbeN * 128)) & 0x3FFFFu) >> 4);
     const uint64_t da = dflags | lo, db = dflags | (lo + (16384 >> 4));
-    // one commit per 4 K blocks (16 MMAs); every commit's phase is waited for, in order, 3 commits late:
-    // bounded run-ahead, and every phase of the barrier is observed (a parity wait must not skip phases)
+    // One commit per 4 K blocks (16 MMAs), commit k on barrier k % 4; commit k - 3 is waited for before
+    // commit k + 1 is issued.  A parity wait is only meaningful while the barrier is at most ONE phase ahead
+    // of its waiter, hence a ring of four barriers: barrier j completes its phase n with commit 4n + j and
+    // cannot complete phase n + 1 before the waiter has seen phase n (it has not issued that commit yet).
     uint32_t commits = 0, waited = 0;
     for (int i = 0; i < iters; ++i) {
       if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_i8(acc, da + 2 * k, db + 2 * k, idesc, 1);
-        if ((i & 3) == 3) umma_commit(bar);
+        if ((i & 3) == 3) umma_commit(bar0 + 8u * (commits & 3));
       }
       __syncwarp();
       if ((i & 3) == 3) {
         ++commits;
-        if (commits - waited > 3) { mbar_wait(bar, waited & 1); ++waited; }
+        if (commits - waited > 3) { mbar_wait(bar0 + 8u * (waited & 3), (waited >> 2) & 1); ++waited; }
       }
     }
-    for (; waited < commits; ++waited) mbar_wait(bar, waited & 1);
+    for (; waited < commits; ++waited) mbar_wait(bar0 + 8u * (waited & 3), (waited >> 2) & 1);
   }
   tc_fence_before();
   __syncthreads();

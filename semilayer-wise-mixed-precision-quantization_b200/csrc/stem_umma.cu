@@ -83,6 +83,7 @@ struct StemArgs {
   const float *bn_a, *bn_b, *act_scales;
   int out_id, out_mode;
   void *out;  // u8 pooled [N,Hp,Wp,64]  |  fp32 conv rows [N,Hc,Wc,64] (SLQ_OUT_F32)
+  uint32_t *out_rowsum;  // [N*Hp*Wp] channel sum of every pooled u8 pixel (or NULL): slq_epilogue.in_rowsum of layer 1
   int units_per_img, total_units;
   long long *trace;  // debug timeline of CTA 0 (slq_debug_set_trace): 24 issuers x cap/24 events
   int trace_cap;
@@ -382,18 +383,29 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
         const uint8_t *row2 = cring + (r2 & (kSfConvRing - 1)) * kSfConvRowBytes;
         uint4 *orow = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) +
                                                 (((long long)n * a.Hp + j) * a.Wp) * 64);
-        for (int idx = et; idx < a.Wp * 4; idx += kSfEpi) {
+        uint32_t *rsrow = a.out_rowsum ? a.out_rowsum + ((long long)n * a.Hp + j) * a.Wp : nullptr;
+        for (int base = et & ~31; base < a.Wp * 4; base += kSfEpi) {  // whole warps walk the loop (shuffles below)
+          const int idx = base + lane;
+          const bool live = idx < a.Wp * 4;
           const int i = idx >> 2, g = (idx & 3) * 16;
-          const int c0 = max(2 * i - 1, 0) * 64 + g, c1 = 2 * i * 64 + g, c2 = min(2 * i + 1, a.Wc - 1) * 64 + g;
-          uint4 m = *reinterpret_cast<const uint4 *>(row0 + c0);
-          auto mx = [&](const uint8_t *ptr) {
-            const uint4 v = *reinterpret_cast<const uint4 *>(ptr);
-            m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
-          };
-          mx(row0 + c1); mx(row0 + c2);
-          mx(row1 + c0); mx(row1 + c1); mx(row1 + c2);
-          mx(row2 + c0); mx(row2 + c1); mx(row2 + c2);
-          orow[idx] = m;
+          uint4 m = make_uint4(0, 0, 0, 0);
+          if (live) {
+            const int c0 = max(2 * i - 1, 0) * 64 + g, c1 = 2 * i * 64 + g, c2 = min(2 * i + 1, a.Wc - 1) * 64 + g;
+            m = *reinterpret_cast<const uint4 *>(row0 + c0);
+            auto mx = [&](const uint8_t *ptr) {
+              const uint4 v = *reinterpret_cast<const uint4 *>(ptr);
+              m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
+            };
+            mx(row0 + c1); mx(row0 + c2);
+            mx(row1 + c0); mx(row1 + c1); mx(row1 + c2);
+            mx(row2 + c0); mx(row2 + c1); mx(row2 + c2);
+            orow[idx] = m;
+          }
+          // channel sum of the pooled pixel: 16 channels per thread, four neighbouring lanes per pixel
+          uint32_t ps = __dp4a(m.x, 0x01010101u, __dp4a(m.y, 0x01010101u, __dp4a(m.z, 0x01010101u, __dp4a(m.w, 0x01010101u, 0u))));
+          ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+          ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+          if (live && rsrow && (idx & 3) == 0) rsrow[i] = ps;
         }
         if (et == 0) stem_trace(a, 18, tn, 6, rc);
       }
@@ -440,8 +452,9 @@ extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace,
   s->wh = reinterpret_cast<__half *>(workspace);
   const int units_per_img = (s->Hp + kSfUnitRows - 1) / kSfUnitRows;
   s->num_ctas = (int)std::min<long long>((long long)N * units_per_img, sm_count());
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  const int cur_dev = current_device();
+  if (cur_dev >= kMaxDevices || !attr_done[cur_dev]) {
     cudaError_t e = cudaFuncSetAttribute(stem_fused_kernel<SLQ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(stem_fused_kernel<SLQ_IN_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
@@ -452,7 +465,7 @@ extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace,
       set_error("slq_stem_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return SLQ_ERR_CUDA;
     }
-    attr_done = true;
+    if (cur_dev < kMaxDevices) attr_done[cur_dev] = true;
   }
   *out = s;
   return SLQ_OK;
@@ -469,13 +482,14 @@ extern "C" int slq_stem_set_weights(slq_stem *s, const float *w, void *stream) {
 
 extern "C" int slq_stem_launch(slq_stem *s, const float *x, const float *bn_a, const float *bn_b,
                                const float *act_scales, int32_t out_id, void *out, int32_t out_mode,
-                               float *f32_scratch, void *stream) {
-  return slq_stem_launch_in(s, x, SLQ_IN_F32, nullptr, bn_a, bn_b, act_scales, out_id, out, out_mode, f32_scratch, stream);
+                               float *f32_scratch, uint32_t *out_rowsum, void *stream) {
+  return slq_stem_launch_in(s, x, SLQ_IN_F32, nullptr, bn_a, bn_b, act_scales, out_id, out, out_mode, f32_scratch,
+                            out_rowsum, stream);
 }
 
 extern "C" int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, const float *norm, const float *bn_a,
                                   const float *bn_b, const float *act_scales, int32_t out_id, void *out,
-                                  int32_t out_mode, float *f32_scratch, void *stream) {
+                                  int32_t out_mode, float *f32_scratch, uint32_t *out_rowsum, void *stream) {
   SLQ_CHECK_ARG(s && x && bn_a && bn_b && out, "slq_stem_launch: null pointer argument");
   SLQ_CHECK_ARG(in_kind == SLQ_IN_F32 || in_kind == SLQ_IN_F16 || in_kind == SLQ_IN_U8, "slq_stem_launch: in_kind %d", in_kind);
   SLQ_CHECK_ARG(in_kind != SLQ_IN_U8 || norm != nullptr, "slq_stem_launch: u8 input needs norm = {mean[3], std[3]}");
@@ -493,20 +507,25 @@ extern "C" int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, c
   a.wh = s->wh;
   a.bn_a = bn_a; a.bn_b = bn_b; a.act_scales = act_scales; a.out_id = out_id; a.out_mode = out_mode;
   a.out = out_mode == SLQ_OUT_U8 ? out : (void *)f32_scratch;
+  a.out_rowsum = out_mode == SLQ_OUT_U8 ? out_rowsum : nullptr;
   a.units_per_img = (s->Hp + kSfUnitRows - 1) / kSfUnitRows;
   a.total_units = s->N * a.units_per_img;
   {
     int cap = 0;
     debug_trace_buffer(&a.trace, &cap);
     a.trace_cap = cap;
+#if SLQ_DEBUG_TRACE
     const char *d = getenv("SLQ_STEM_DBG");
     a.dbg = d ? atoi(d) : 0;
+#else
+    a.dbg = 0;
+#endif
   }
   if (in_kind == SLQ_IN_F32) stem_fused_kernel<SLQ_IN_F32><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   else if (in_kind == SLQ_IN_F16) stem_fused_kernel<SLQ_IN_F16><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   else stem_fused_kernel<SLQ_IN_U8><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   SLQ_LAUNCH_CHECK();
   if (out_mode == SLQ_OUT_F32)
-    return launch_stem_pool(f32_scratch, s->N, s->Hc, s->Wc, s->Hp, s->Wp, act_scales, out_id, out, SLQ_OUT_F32, st);
+    return launch_stem_pool(f32_scratch, s->N, s->Hc, s->Wc, s->Hp, s->Wp, act_scales, out_id, out, SLQ_OUT_F32, nullptr, st);
   return SLQ_OK;
 }

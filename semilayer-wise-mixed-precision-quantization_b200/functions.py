@@ -148,18 +148,80 @@ def channel_wise_quantizationperchan(tensor, bit, i):
     return tensor
 
 
-class PackedModel:
-    """Result of quantize_model: all jobs of all tensors in ONE launch.  Arrays are in launch order (jobs
-    sorted by row length class); ``perm[j]`` is the position of launch-order job j in the caller's order
-    (tensors in the order given, rows in the order given)."""
+class QuantPlan:
+    """A whole bit assignment -- rows of SEVERAL weight tensors -- prepared as ONE multi-tensor job table on
+    the device (slq_quantize_jobs).  ``run()`` is then a single kernel launch with no host work in front of it
+    (the reference makes one quantize_wgt call, 7 launches and 2 syncs, per row: resnet50_main.py:189-197).
 
-    def __init__(self, perm, item_of, rows, bits, K, offsets, blob, z, s32, status):
-        self.perm, self.item_of, self.rows, self.bits, self.K = perm, item_of, rows, bits, K
-        self.offsets, self.blob, self.z, self.s32, self.status = offsets, blob, z, s32, status
+    ``items``: list of ``(tensor, rows, bits)`` with contiguous fp32 CUDA tensors ``[Cout, ...]`` on one
+    device.  Arrays are in launch order (jobs sorted by row-length class); ``perm[j]`` is the position of
+    launch-order job j in the caller's order (tensors in the order given, rows in the order given)."""
+
+    def __init__(self, items, want_codes=True, div_mode=None):
+        if not items:
+            raise ValueError("QuantPlan: no tensors")
+        dev = items[0][0].device
+        rowp, Ks, bits_all, rows_all, item_of = [], [], [], [], []
+        for i, (t, rows, bits) in enumerate(items):
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda or t.device != dev:
+                raise TypeError("QuantPlan needs contiguous float32 CUDA tensors on one device")
+            K = t[0].numel()
+            if K % 4 != 0 or K > 4608 or t.data_ptr() % 16 != 0:
+                raise ValueError("QuantPlan: row length %d unsupported (use quantize_rows)" % K)
+            r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
+            b = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)
+            if r.size != b.size:
+                raise ValueError("rows and bits must have the same length")
+            if r.size and (r.min() < 0 or r.max() >= t.shape[0]):
+                raise IndexError("row index out of range")
+            if b.size and (b.min() < 1 or b.max() > 8):
+                raise ValueError("bit-width must be in 1..8")
+            rowp.append(np.uint64(t.data_ptr()) + (r * (4 * K)).astype(np.uint64))
+            Ks.append(np.full(r.size, K, np.int32))
+            bits_all.append(b)
+            rows_all.append(r)
+            item_of.append(np.full(r.size, i, np.int32))
+        rowp, Ks, bits_all = np.concatenate(rowp), np.concatenate(Ks), np.concatenate(bits_all)
+        rows_all, item_of = np.concatenate(rows_all), np.concatenate(item_of)
+        n = rowp.size
+        if n == 0:
+            raise ValueError("QuantPlan: no rows")
+        cls = (Ks > 288).astype(np.int8) + (Ks > 1152).astype(np.int8)
+        perm = np.argsort(cls, kind="stable")
+        self.counts = [int(c) for c in np.bincount(cls, minlength=3)]
+        sizes = (np.where(bits_all == 4, (Ks + 1) // 2, np.where(bits_all == 2, (Ks + 3) // 4, Ks)).astype(np.int64) + 15) // 16 * 16
+        sizes_p = sizes[perm]
+        offs = np.zeros(n, np.int64)
+        offs[1:] = np.cumsum(sizes_p)[:-1]
+        self.div_mode = _div_mode_for(items[0][0], div_mode)
+        self.items, self.device, self.n = items, dev, n
+        self.perm, self.item_of, self.rows, self.bits, self.K, self.offsets = \
+            perm, item_of[perm], rows_all[perm], bits_all[perm], Ks[perm], offs
+        with torch.cuda.device(dev):
+            self.blob = torch.empty(max(int(sizes_p.sum()), 16), dtype=torch.uint8, device=dev) if want_codes else None
+            jobs = np.empty(n, _QJOB)
+            jobs["row"], jobs["K"], jobs["bit"] = rowp[perm], Ks[perm], bits_all[perm]
+            jobs["codes"] = (np.uint64(self.blob.data_ptr()) + offs.astype(np.uint64)) if want_codes else 0
+            self.jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)  # the one host->device copy
+            self.z = torch.empty(n, dtype=torch.int32, device=dev)
+            self.s32 = torch.empty(n, dtype=torch.float32, device=dev)
+            self.status = torch.empty(n, dtype=torch.int32, device=dev)
 
     @property
     def nbytes(self):
         return 0 if self.blob is None else int(self.blob.numel())
+
+    def run(self, write_back=True):
+        """ONE launch; nothing is synchronised."""
+        with torch.cuda.device(self.device):
+            L.check(L.lib().slq_quantize_jobs(self.jobs_d.data_ptr(), self.counts[0], self.counts[1], self.counts[2],
+                                              self.div_mode, 1 if write_back else 0, self.z.data_ptr(),
+                                              self.s32.data_ptr(), self.status.data_ptr(),
+                                              L.current_stream(self.device)))
+        if write_back:
+            for t, _r, _b in self.items:
+                resnet.note_weight_write(t)
+        return self
 
     def check(self):
         """The one synchronisation: raises ZeroDivisionError like the reference (functions.py:40) if any
@@ -170,72 +232,18 @@ class PackedModel:
         return st
 
 
+PackedModel = QuantPlan  # what quantize_model returns: the plan, with its outputs filled in
 _QJOB = np.dtype([("row", "<u8"), ("codes", "<u8"), ("K", "<i4"), ("bit", "<i4")])
 
 
 def quantize_model(items, write_back=True, want_codes=True, div_mode=None, check=True):
-    """Quantises rows of SEVERAL weight tensors -- a whole model's bit assignment -- in ONE kernel launch
-    (slq_quantize_jobs): ``items`` is a list of ``(tensor, rows, bits)`` with contiguous fp32 CUDA tensors
-    ``[Cout, ...]`` on one device.  The reference makes one quantize_wgt call (7 launches, 2 syncs) per row
-    (resnet50_main.py:189-197).  One host->device copy of the job table, one launch, and -- with ``check`` --
-    one synchronisation at the end.  Returns PackedModel."""
-    lib = L.lib()
-    if not items:
-        raise ValueError("quantize_model: no tensors")
-    dev = items[0][0].device
-    rowp, Ks, bits_all, rows_all, item_of = [], [], [], [], []
-    for i, (t, rows, bits) in enumerate(items):
-        if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda or t.device != dev:
-            raise TypeError("quantize_model needs contiguous float32 CUDA tensors on one device")
-        K = t[0].numel()
-        if K % 4 != 0 or K > 4608 or t.data_ptr() % 16 != 0:
-            raise ValueError("quantize_model: row length %d unsupported (use quantize_rows)" % K)
-        r = np.ascontiguousarray(rows, dtype=np.int64).reshape(-1)
-        b = np.ascontiguousarray(bits, dtype=np.int32).reshape(-1)
-        if r.size != b.size:
-            raise ValueError("rows and bits must have the same length")
-        if r.size and (r.min() < 0 or r.max() >= t.shape[0]):
-            raise IndexError("row index out of range")
-        if b.size and (b.min() < 1 or b.max() > 8):
-            raise ValueError("bit-width must be in 1..8")
-        rowp.append(np.uint64(t.data_ptr()) + (r * (4 * K)).astype(np.uint64))
-        Ks.append(np.full(r.size, K, np.int32))
-        bits_all.append(b)
-        rows_all.append(r)
-        item_of.append(np.full(r.size, i, np.int32))
-    rowp, Ks, bits_all = np.concatenate(rowp), np.concatenate(Ks), np.concatenate(bits_all)
-    rows_all, item_of = np.concatenate(rows_all), np.concatenate(item_of)
-    n = rowp.size
-    if n == 0:
-        raise ValueError("quantize_model: no rows")
-    cls = (Ks > 288).astype(np.int8) + (Ks > 1152).astype(np.int8)
-    perm = np.argsort(cls, kind="stable")
-    counts = np.bincount(cls, minlength=3)
-    sizes = (np.where(bits_all == 4, (Ks + 1) // 2, np.where(bits_all == 2, (Ks + 3) // 4, Ks)).astype(np.int64) + 15) // 16 * 16
-    sizes_p = sizes[perm]
-    offs = np.zeros(n, np.int64)
-    offs[1:] = np.cumsum(sizes_p)[:-1]
-    dm = _div_mode_for(items[0][0], div_mode)
-    with torch.cuda.device(dev):
-        blob = torch.empty(max(int(sizes_p.sum()), 16), dtype=torch.uint8, device=dev) if want_codes else None
-        jobs = np.empty(n, _QJOB)
-        jobs["row"], jobs["K"], jobs["bit"] = rowp[perm], Ks[perm], bits_all[perm]
-        jobs["codes"] = (np.uint64(blob.data_ptr()) + offs.astype(np.uint64)) if want_codes else 0
-        jobs_d = torch.from_numpy(jobs.view(np.uint8).reshape(-1)).to(dev)
-        z = torch.empty(n, dtype=torch.int32, device=dev)
-        s32 = torch.empty(n, dtype=torch.float32, device=dev)
-        status = torch.empty(n, dtype=torch.int32, device=dev)
-        L.check(lib.slq_quantize_jobs(jobs_d.data_ptr(), int(counts[0]), int(counts[1]), int(counts[2]), dm,
-                                      1 if write_back else 0, z.data_ptr(), s32.data_ptr(), status.data_ptr(),
-                                      L.current_stream(dev)))
-    if write_back:
-        for t, _r, _b in items:
-            resnet.note_weight_write(t)
-    pm = PackedModel(perm, item_of[perm], rows_all[perm], bits_all[perm], Ks[perm], offs, blob, z, s32, status)
-    pm._keepalive = jobs_d  # the kernel reads the table asynchronously
+    """Quantises rows of several weight tensors -- a whole model's bit assignment -- in ONE kernel launch:
+    one host->device copy of the job table, one launch, and -- with ``check`` -- one synchronisation at the
+    end.  Returns the QuantPlan (keep it and call ``run()`` again to re-quantise without any host work)."""
+    plan = QuantPlan(items, want_codes=want_codes, div_mode=div_mode).run(write_back=write_back)
     if check:
-        pm.check()
-    return pm
+        plan.check()
+    return plan
 
 
 # ==============================================================================================

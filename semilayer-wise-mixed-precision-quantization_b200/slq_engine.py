@@ -170,6 +170,16 @@ class Engine:
         for op in self.ops:
             max_out = max(max_out, op.M * op.Cout)
         self.final_id, self.final_hw, self.final_c = x_id, h * w, self.act[x_id].shape[3]
+        # per-pixel channel sums ("rowsum") of every u8 activation that feeds a conv: ONE pool, zeroed by one
+        # memset at the start of a pass; producers accumulate into their slice, consumers gather their
+        # window sums from it (slq_epilogue.in_rowsum / out_rowsum)
+        feeds = sorted({op.in_id for op in self.ops})
+        pixels = {i: self.act[i].shape[0] * self.act[i].shape[1] * self.act[i].shape[2] for i in feeds}
+        self.rowsum_pool = torch.zeros(sum(pixels.values()), dtype=torch.int32, device=dev)
+        self.rowsum, pos = {}, 0
+        for i in feeds:
+            self.rowsum[i] = self.rowsum_pool[pos:pos + pixels[i]]
+            pos += pixels[i]
         self.f32_scratch = torch.empty(max_out, dtype=torch.float32, device=dev)
         self.act_scales = torch.ones(len(self.act), dtype=torch.float32, device=dev)
         self.absmax_tmp = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -315,9 +325,11 @@ class Engine:
         e = op.epi.get(key)
         if e is None:
             res = self.act[op.res_id].data_ptr() if op.res_id >= 0 else None
+            rs_out = self.rowsum.get(op.out_id) if mode == L.OUT_U8 else None
             e = L.Epilogue(op.wscale.data_ptr(), op.zf.data_ptr(), op.bias.data_ptr(),
                            self.act_scales.data_ptr(), op.in_id, op.out_id, op.res_id, res,
-                           1 if op.res_signed else 0, out_ptr, out_S, mode, 1 if op.relu else 0)
+                           1 if op.res_signed else 0, out_ptr, out_S, mode, 1 if op.relu else 0,
+                           self.rowsum[op.in_id].data_ptr(), L.ptr(rs_out))
             op.epi[key] = e
         return e
 
@@ -366,6 +378,7 @@ class Engine:
                     torch.maximum(self.act_scales[idx:idx + 1], old[idx:idx + 1], out=self.act_scales[idx:idx + 1])
 
             n0 = self.act[0].numel()
+            self._zero_rowsums(st)
             self._stem(x.data_ptr(), f32.data_ptr(), L.OUT_F32, st)
             L.check(lib.slq_absmax_scale(f32.data_ptr(), n0, sc, 0, 255, tmp, st))
             settle(0)
@@ -410,6 +423,7 @@ class Engine:
     def launch_all(self, x_ptr, st):
         lib = self.lib
         sc = self.act_scales.data_ptr()
+        self._zero_rowsums(st)
         self._stem(x_ptr, self.act[0].data_ptr(), L.OUT_U8, st)
         for op in self.ops:
             mode = L.OUT_S8 if op.signed else L.OUT_U8
@@ -418,7 +432,10 @@ class Engine:
         L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
                                      sc, self.final_id, self.fc_w.data_ptr(), self.fc_b.data_ptr(),
                                      self.logits.shape[1], self.pooled.data_ptr(), self.logits.data_ptr(), st))
-        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 2
+        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 2  # + one memset node
+
+    def _zero_rowsums(self, st):
+        L.check(self.lib.slq_zero_async(self.rowsum_pool.data_ptr(), self.rowsum_pool.numel() * 4, st))
 
     def _stem(self, x_ptr, out_ptr, mode, st):
         lib, sc = self.lib, self.act_scales.data_ptr()
@@ -426,11 +443,12 @@ class Engine:
             kind = getattr(self, "in_kind", L.IN_F32)
             norm = ctypes.cast(self.norm, ctypes.c_void_p) if kind == L.IN_U8 else None
             L.check(lib.slq_stem_launch_in(self.stem, x_ptr, kind, norm, self.stem_a.data_ptr(), self.stem_b.data_ptr(),
-                                           sc, 0, out_ptr, mode, self.stem_scratch.data_ptr(), st))
+                                           sc, 0, out_ptr, mode, self.stem_scratch.data_ptr(),
+                                           self.rowsum[0].data_ptr(), st))
         else:
             L.check(lib.slq_stem_forward(x_ptr, self.N, self.H, self.W, self.stem_w.data_ptr(),
                                          self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
-                                         self.stem_scratch.data_ptr(), out_ptr, mode, st))
+                                         self.stem_scratch.data_ptr(), out_ptr, mode, self.rowsum[0].data_ptr(), st))
 
     # ------------------------------------------------------------------------------------------
     def capture_graph(self, x_static):

@@ -30,7 +30,8 @@ class Epilogue(ctypes.Structure):
     _fields_ = [("wscale", _vp), ("zf", _vp), ("bias", _vp), ("act_scales", _vp),
                 ("in_id", _i32), ("out_id", _i32), ("res_id", _i32),
                 ("res", _vp), ("res_signed", _i32),
-                ("out", _vp), ("out_S", _vp), ("out_mode", _i32), ("relu", _i32)]
+                ("out", _vp), ("out_S", _vp), ("out_mode", _i32), ("relu", _i32),
+                ("in_rowsum", _vp), ("out_rowsum", _vp)]
 
 
 # name -> (restype, argtypes); mirrors include/slq.h one to one (tests check the export list)
@@ -54,13 +55,14 @@ SIGNATURES = {
     "slq_conv_destroy": (None, [_vp]),
     "slq_conv_launch": (ctypes.c_int, [_vp, ctypes.POINTER(Epilogue), _vp]),
     "slq_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
-    "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp]),
+    "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "slq_zero_async": (ctypes.c_int, [_vp, _i64, _vp]),
     "slq_stem_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "slq_stem_create": (ctypes.c_int, [_i32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),
     "slq_stem_destroy": (None, [_vp]),
     "slq_stem_set_weights": (ctypes.c_int, [_vp, _vp, _vp]),
-    "slq_stem_launch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
-    "slq_stem_launch_in": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp]),
+    "slq_stem_launch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "slq_stem_launch_in": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "slq_tail_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "slq_absmax_scale": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "slq_quantize_act": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),

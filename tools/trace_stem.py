@@ -23,7 +23,7 @@ buf = torch.zeros(3 * cap, dtype=torch.int64, device="cuda")
 for rep in range(2):
     buf.zero_(); torch.cuda.synchronize()
     lib.slq_debug_set_trace(buf.data_ptr() if rep == 1 else None, cap)
-    L.check(lib.slq_stem_launch(h, x.data_ptr(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), 0, out.data_ptr(), L.OUT_U8, scratch.data_ptr(), L.current_stream()))
+    L.check(lib.slq_stem_launch(h, x.data_ptr(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), 0, out.data_ptr(), L.OUT_U8, scratch.data_ptr(), None, L.current_stream()))
     torch.cuda.synchronize()
 lib.slq_debug_set_trace(None, 0)
 hh = buf.cpu().numpy().reshape(cap, 3)
