@@ -550,6 +550,49 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int tn = 0;
     long long wepi = 0;
     const long long tstart_clk = clock64();
+    // S[m] = sum over the conv window of the per-pixel channel sums the producing kernel accumulated
+    // (slq_epilogue.in_rowsum).  1x1 stride-1 layers -- all the epilogue-bound ones -- read one value at index m;
+    // the others split m into (image, row, column) with a float reciprocal (M < 2^24: exact after one fix-up).
+    const bool same_grid = g.kh == 1 && g.stride == 1;
+    const float inv_hw = __frcp_rn((float)(g.Ho * g.Wo)), inv_wo = __frcp_rn((float)g.Wo);
+    auto window_sum = [&](int mm) -> uint32_t {
+      if (mm >= g.M) return 0u;
+      if (same_grid) return __ldg(e.in_rowsum + mm);
+      const int hw = g.Ho * g.Wo;
+      int n_img, rem, ho, wo;
+      if (g.M < (1 << 24)) {  // every index is an exact float: the reciprocal quotient is off by at most one
+        n_img = (int)((float)mm * inv_hw);
+        rem = mm - n_img * hw;
+        if (rem < 0) { --n_img; rem += hw; } else if (rem >= hw) { ++n_img; rem -= hw; }
+        ho = (int)((float)rem * inv_wo);
+        wo = rem - ho * g.Wo;
+        if (wo < 0) { --ho; wo += g.Wo; } else if (wo >= g.Wo) { ++ho; wo -= g.Wo; }
+      } else {
+        n_img = mm / hw; rem = mm - n_img * hw;
+        ho = rem / g.Wo; wo = rem - ho * g.Wo;
+      }
+      const uint32_t *rs = e.in_rowsum + (long long)n_img * g.H * g.W;
+      if (g.kh == 1) return __ldg(rs + (ho * g.stride) * g.W + wo * g.stride);
+      const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
+      uint32_t sum = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hi = h0 + r;
+        if (hi < 0 || hi >= g.H) continue;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int wi = w0 + q;
+          if (wi >= 0 && wi < g.W) sum += __ldg(rs + hi * g.W + wi);
+        }
+      }
+      return sum;
+    };
+    uint32_t S_next = 0;
+    if (team < walk.count) {
+      int mt0, nt0;
+      walk.at(team, mt0, nt0);
+      S_next = window_sum(mt0 * kTileM + row);
+    }
     for (int it = team; it < walk.count; it += 2) {
       int m_tile, n_tile;
       walk.at(it, m_tile, n_tile);
@@ -568,32 +611,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         last_n_tile = n_tile;
         named_bar_sync(1 + team, kTeam);
       }
-      // window sum of the INPUT activation for this thread's output pixel, from the per-pixel channel sums the
-      // producing kernel accumulated (<= 9 loads, issued before the wait for the accumulator)
+      // window sum of the INPUT activation for this thread's output pixel: gathered one tile AHEAD (the loads
+      // of tile it + 2 are in flight while tile it is converted), so their latency is never exposed
       const long long m = (long long)m_tile * kTileM + row;
       const bool valid = m < g.M;
-      uint32_t S_raw = 0;
-      if (valid) {
-        const int hw = g.Ho * g.Wo;
-        const int n_img = (int)(m / hw);
-        const int rem = (int)(m - (long long)n_img * hw);
-        const int ho = rem / g.Wo, wo = rem - ho * g.Wo;
-        const uint32_t *rs = e.in_rowsum + (long long)n_img * g.H * g.W;
-        if (g.kh == 1) {
-          S_raw = __ldg(rs + (ho * g.stride) * g.W + wo * g.stride);
-        } else {
-          const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
-#pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const int hi = h0 + r;
-            if (hi < 0 || hi >= g.H) continue;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-              const int wi = w0 + q;
-              if (wi >= 0 && wi < g.W) S_raw += __ldg(rs + hi * g.W + wi);
-            }
-          }
-        }
+      const uint32_t S_raw = S_next;
+      if (it + 2 < walk.count) {
+        int mt2, nt2;
+        walk.at(it + 2, mt2, nt2);
+        S_next = window_sum(mt2 * kTileM + row);
       }
       mbar_wait_stat(tfull_bar(tb), ph, wepi, kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0);
       tc_fence_after();
@@ -940,6 +966,9 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
   // wide tiles only where the 128-channel tiling has to stream its weights anyway (K-heavy layers)
   c->wide_ok = (d->impl == SLQ_IMPL_UMMA && c->g_wide.bn_ch == 256 && c->swizzle == 128 &&
                 !make_plan(c->g, c->swizzle, false).b_resident) ? 1 : 0;
+#if SLQ_DEBUG_TRACE
+  if (getenv("SLQ_NO_WIDE")) c->wide_ok = 0;  // A/B timing against the 128-channel tiling (debug build only)
+#endif
   c->out_ptr = nullptr;
   c->res_ptr = nullptr;
   const bool can_tile = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0;

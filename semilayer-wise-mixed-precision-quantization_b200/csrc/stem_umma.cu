@@ -32,8 +32,9 @@
 
 struct slq_stem {
   int N, H, W, Hc, Wc, Hp, Wp;
-  __half *wh;  // [64, 192] fp16, K order (c*7 + r)*8 + s, zero padded
+  __half *wh;  // [64, 192] fp16, zero padded; K order of the kernel in use (see the two weight kernels)
   int num_ctas;
+  int use_ts;  // 1: stem_ts_kernel (A operand in TMEM; needs 16-byte input rows: W % 16 == 0), 0: stem_fused_kernel
 };
 
 namespace slq {
@@ -420,6 +421,366 @@ __global__ void __launch_bounds__(kSfThreads, 1) stem_fused_kernel(const StemArg
   }
 }
 
+// ================================================================================================
+// Stem v2: A operand in TENSOR MEMORY (tcgen05.mma TS form)
+// ================================================================================================
+// The 7x7 stride-2 conv as an implicit GEMM whose K dimension is cut into "pair slabs": slab (c, t) is the
+// [128 output columns q] x [16 halfs] matrix  { x[c][2t][2q-3 .. 2q+4], x[c][2t+1][2q-3 .. 2q+4] }
+// (input-row pair t of channel c).  Conv row p needs the four pairs t = p-2 .. p+1: pair i = t - p + 2
+// multiplies the filter rows r = 2i-1 (first row of the pair; r = -1 -> zero weights) and r = 2i, i.e. a
+// FIXED 64 x 16 weight slice per (c, i).  Going from conv row p to p+1 therefore adds ONE new pair (3
+// slabs) and retires one -- round 1 rebuilt all 21 (c, r) chunks of every conv row in shared memory
+// (2688 16-byte chunks per row through LDS.32 / STS.128; the stem was bound by exactly that).
+//   producer (warp 0)    TMA bulk copies of the raw input rows of pair t into an 8-deep staging ring
+//   builders (8 warps)   staging -> fp16 rows (each element converted once) -> the thread that owns output
+//                        column q writes its 16-byte window of each of the six rows straight into the
+//                        slab's TMEM columns (tcgen05.st): the A operand never exists in shared memory
+//   MMA (4 warps)        conv row rc -> warp rc & 3, accumulator rc & 3: 12 tcgen05.mma.kind::f16
+//                        (A from TMEM, 64 x 16 weight slices resident in shared memory, M128 N64 K16)
+//   epilogue (8 warps)   tcgen05.ld -> folded BN + ReLU -> u8 -> 4-row ring -> 3x3/s2 max-pool -> store
+// TMEM: columns [0, 256) four accumulators; [256, 448) eight pair slots x 3 channels x 8 columns.
+
+constexpr int kTsSlots = 8;                       // staged input-row pairs == TMEM pair slots
+constexpr int kTsRowP = 264;                      // halfs per converted row: column cc = w + 3, w in [-3, 2*127+4]
+constexpr int kTsMaxRowBytes = 1024;              // W <= 256 fp32 elements
+constexpr int kTsStageBytes = 6 * kTsMaxRowBytes; // one pair: 3 channels x 2 rows, raw
+constexpr int kTsStageOff = 0;
+constexpr int kTsRowBufOff = kTsStageOff + kTsSlots * kTsStageBytes;
+constexpr int kTsRowBufBytes = 2 * 6 * kTsRowP * 2;   // double-buffered fp16 rows of one pair
+constexpr int kTsBOff = ((kTsRowBufOff + kTsRowBufBytes + 1023) / 1024) * 1024;
+constexpr int kTsConvOff = kTsBOff + kSfBBytes;
+constexpr int kTsPrmOff = kTsConvOff + kSfConvRing * kSfConvRowBytes;
+constexpr int kTsBarOff = kTsPrmOff + 64 * 8;
+constexpr int kTsSmemBytes = 1024 + kTsBarOff + 512;
+constexpr int kTsBuildW = 8, kTsMmaW = 4, kTsEpiW = 8;
+constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW;  // producer + builders + MMA + epilogue = 21
+constexpr int kTsThreads = kTsWarps * 32;
+constexpr int kTsBuilders = kTsBuildW * 32, kTsEpi = kTsEpiW * 32;
+constexpr int kTsAccCols = 64, kTsSlabBase = 256, kTsSlotCols = 24;
+constexpr int kTsTmemCols = 512;
+static_assert(kTsSmemBytes <= 232448, "stem v2 exceeds 227 KB of shared memory");
+
+// w fp32 [64, 3, 7, 7] -> wh fp16 [64, 192]: wh[oc][c*64 + ch*8 + s] = w[oc][c][ch-1][s]  (ch = 2i + j is
+// the row of pair i: filter row r = ch - 1; ch = 0 and s = 7 are zero)
+__global__ void stem_weights_ts_kernel(const float *__restrict__ w, __half *__restrict__ wh) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 64 * kSfK) return;
+  const int k = idx % kSfK, oc = idx / kSfK;
+  const int c = k >> 6, ch = (k >> 3) & 7, s = k & 7;
+  float v = 0.f;
+  if (ch >= 1 && s < 7) v = w[((oc * 3 + c) * 7 + (ch - 1)) * 7 + s];
+  wh[idx] = __float2half_rn(v);
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem], fp16 operands, fp32 accumulate
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <int IN>
+__global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + kTsBarOff;
+  auto sfull_bar = [&](int s) { return bar_base + 8u * s; };          // raw rows of a pair landed (TMA tx)
+  auto sempty_bar = [&](int s) { return bar_base + 8u * (8 + s); };   // builders have converted them (8 warps)
+  auto pfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };   // pair slabs written to TMEM (8 warps)
+  auto pfree_bar = [&](int s) { return bar_base + 8u * (24 + s); };   // the 4 conv rows using the pair are done (4 commits)
+  auto tfull_bar = [&](int b) { return bar_base + 8u * (32 + b); };   // accumulator ready (commit)
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (36 + b); };  // accumulator drained (256 threads)
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kTsBarOff + 8 * 40);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  constexpr int ESZ = IN == SLQ_IN_F32 ? 4 : (IN == SLQ_IN_F16 ? 2 : 1);
+  const int row_bytes = a.W * ESZ;
+
+  // ---- one-time setup -------------------------------------------------------------------------
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kTsSlots; ++s) {
+      mbar_init(sfull_bar(s), 1);
+      mbar_init(sempty_bar(s), kTsBuildW);
+      mbar_init(pfull_bar(s), kTsBuildW);
+      mbar_init(pfree_bar(s), 4);
+    }
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), kTsEpi);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void *)tmem_slot)),
+                 "r"(kTsTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // converted-row buffers: the pad columns are never written again; weights + BN constants
+  for (int i = threadIdx.x; i < kTsRowBufBytes / 16; i += blockDim.x)
+    reinterpret_cast<uint4 *>(smem + kTsRowBufOff)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < 64 * kSfChunks; i += blockDim.x) {
+    const int oc = i / kSfChunks, j = i % kSfChunks;
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.wh + oc * kSfK + j * 8));
+    const int kb = j >> 3, cj = j & 7;  // kb = channel c, cj = 2i + j: 32 bytes per pair i inside the 128-byte row
+    *reinterpret_cast<uint4 *>(smem + kTsBOff + kb * 8192 + oc * 128 + ((cj ^ (oc & 7)) << 4)) = v;
+  }
+  if (threadIdx.x < 64) {  // u8 output: the re-quantisation multiply is folded into the BN constants
+    const float inv = a.out_mode == SLQ_OUT_F32 ? 1.f : __fdiv_rn(1.0f, a.act_scales[a.out_id]);
+    reinterpret_cast<float2 *>(smem + kTsPrmOff)[threadIdx.x] =
+        make_float2(__fmul_rn(a.bn_a[threadIdx.x], inv), __fmul_rn(a.bn_b[threadIdx.x], inv));
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Every role walks the same units; running counters: rc = conv rows so far, g = pairs so far.  A unit
+  // of R conv rows consumes R + 3 pairs (the first row needs four), so row rc of the u-th unit uses the
+  // pairs g_lo .. g_lo + 3 with g_lo = rc + 3 u.
+  if (warp == 0) {
+    // ================================ producer: raw rows -> staging ring ======================
+    int g = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+      int n, j0, j1, p0, p1;
+      unit_rows(a, u, n, j0, j1, p0, p1);
+      const uint8_t *xn = reinterpret_cast<const uint8_t *>(a.x) + (long long)n * 3 * a.H * row_bytes;
+      for (int t = p0 - 2; t <= p1; ++t, ++g) {
+        const int s = g & (kTsSlots - 1);
+        mbar_wait(sempty_bar(s), (uint32_t)(((g >> 3) & 1) ^ 1));
+        if (elect_one()) {
+          const int h0 = 2 * t;
+          const int live = (h0 >= 0 && h0 < a.H ? 1 : 0) + (h0 + 1 >= 0 && h0 + 1 < a.H ? 1 : 0);
+          if (live == 0) {
+            mbar_arrive(sfull_bar(s));  // a pair of padding rows: nothing to copy
+          } else {
+            mbar_expect_tx(sfull_bar(s), (uint32_t)(3 * live * row_bytes));
+            for (int c = 0; c < 3; ++c)
+              for (int j = 0; j < 2; ++j) {
+                const int h = h0 + j;
+                if (h < 0 || h >= a.H) continue;
+                bulk_copy_g2s(smem_base + kTsStageOff + s * kTsStageBytes + (c * 2 + j) * kTsMaxRowBytes,
+                              xn + ((long long)c * a.H + h) * row_bytes, (uint32_t)row_bytes, sfull_bar(s));
+              }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp <= kTsBuildW) {
+    // ================================ builders ================================================
+    const int bt = threadIdx.x - 32;                 // 0..255
+    const int quarter = warp & 3;                    // the TMEM lanes this warp may touch
+    const int sub = (warp - 1) >> 2;                 // which three of the six (c, j) rows of a pair it writes
+    const int q = quarter * 32 + lane;               // output column == TMEM lane
+    __half *rowbuf = reinterpret_cast<__half *>(smem + kTsRowBufOff);
+    const int w4 = a.W >> 2, groups = 6 * w4;        // 4-element groups of the six rows
+    int g = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+      int n, j0, j1, p0, p1;
+      unit_rows(a, u, n, j0, j1, p0, p1);
+      for (int t = p0 - 2; t <= p1; ++t, ++g) {
+        const int s = g & (kTsSlots - 1);
+        const uint32_t ph = (uint32_t)((g >> 3) & 1);
+        __half *rb = rowbuf + (g & 1) * 6 * kTsRowP;
+        mbar_wait(sfull_bar(s), ph);
+        // 1. raw -> fp16, every element once
+        const uint8_t *stg = smem + kTsStageOff + s * kTsStageBytes;
+        for (int idx = bt; idx < groups; idx += kTsBuilders) {
+          const int r6 = idx / w4, c4 = idx - r6 * w4;
+          const int h = 2 * t + (r6 & 1), c = r6 >> 1;
+          float f[4] = {0.f, 0.f, 0.f, 0.f};
+          if (h >= 0 && h < a.H) {
+            const uint8_t *src = stg + r6 * kTsMaxRowBytes + c4 * 4 * ESZ;
+            if (IN == SLQ_IN_F32) {
+              const float4 v = *reinterpret_cast<const float4 *>(src);
+              f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+            } else if (IN == SLQ_IN_F16) {
+              const uint2 v = *reinterpret_cast<const uint2 *>(src);
+              f[0] = stem_pixel<IN>(v.x & 0xffffu, 0.f, 1.f); f[1] = stem_pixel<IN>(v.x >> 16, 0.f, 1.f);
+              f[2] = stem_pixel<IN>(v.y & 0xffffu, 0.f, 1.f); f[3] = stem_pixel<IN>(v.y >> 16, 0.f, 1.f);
+            } else {
+              const uint32_t v = *reinterpret_cast<const uint32_t *>(src);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) f[e] = stem_pixel<IN>((v >> (8 * e)) & 255u, a.nmean[c], a.nstd[c]);
+            }
+          }
+          __half *dst = rb + r6 * kTsRowP + 3 + 4 * c4;  // 2-byte aligned (cc = w + 3)
+          dst[0] = __float2half_rn(f[0]);
+          *reinterpret_cast<__half2 *>(dst + 1) = __floats2half2_rn(f[1], f[2]);
+          dst[3] = __float2half_rn(f[3]);
+        }
+        named_bar_sync(1, kTsBuilders);  // rows complete; also: nobody still reads the buffer of pair g - 2
+        if (lane == 0) mbar_arrive(sempty_bar(s));  // the staging slot may be refilled
+        // 2. the pair's TMEM slot must be free: the four conv rows that used pair g - 8 have completed
+        if (g >= kTsSlots) mbar_wait(pfree_bar(s), ph ^ 1);
+        tc_fence_after();
+        // 3. this thread's 16-byte windows x[c][h][2q-3 .. 2q+4] -> the slab's TMEM columns
+        const uint32_t tslab = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTsSlabBase + s * kTsSlotCols;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int r6 = sub * 3 + k;  // = c * 2 + j
+          const uint32_t *src = reinterpret_cast<const uint32_t *>(rb + r6 * kTsRowP + 2 * q);
+          tmem_st4(tslab + (r6 >> 1) * 8 + (r6 & 1) * 4, src[0], src[1], src[2], src[3]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pfull_bar(s));
+      }
+    }
+  } else if (warp <= kTsBuildW + kTsMmaW) {
+    // ================================ MMA issuers (convergent warps, elected lane) =============
+    const int mw = warp - (kTsBuildW + 1);  // conv rows with rc % 4 == mw
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint64_t db0 = make_smem_desc<128>(smem_base + kTsBOff);
+    int rc = 0, u_ord = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++u_ord) {
+      int n, j0, j1, p0, p1;
+      unit_rows(a, u, n, j0, j1, p0, p1);
+      for (int p = p0; p < p1; ++p, ++rc) {
+        if ((rc & 3) != mw) continue;
+        const int acc = rc & 3;
+        const int g_lo = rc + 3 * u_ord;
+        if (rc >= 4) mbar_wait(tempty_bar(acc), (uint32_t)(((rc >> 2) & 1) ^ 1));
+        // pairs complete in order: the newest one implies the three before it
+        mbar_wait(pfull_bar((g_lo + 3) & (kTsSlots - 1)), (uint32_t)(((g_lo + 3) >> 3) & 1));
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t ta = tmem_u + kTsSlabBase + ((g_lo + i) & (kTsSlots - 1)) * kTsSlotCols;
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              umma_f16_ts(tmem_u + acc * kTsAccCols, ta + c * 8, db0 + (uint64_t)(c * (8192 >> 4) + 2 * i), idesc,
+                          (uint32_t)((i | c) != 0));
+          }
+          // a pair slab is read by the MMAs of FOUR conv rows, issued by four different threads, and a commit
+          // only tracks its own thread's MMAs: every row arrives once on each of its four pairs ...
+#pragma unroll
+          for (int i = 0; i < 4; ++i) umma_commit(pfree_bar((g_lo + i) & (kTsSlots - 1)));
+          // ... and the rows at the ends of a unit stand in for the users their pairs do not have
+          // (the first pair of a unit is used by 1 row, the second by 2, the third by 3; same at the end)
+          // pair k of a unit has min(k, 3) + 1 users at its start and as few at its end: the first row adds the
+          // 3 - i arrivals its pair i lacks, the last row the i arrivals its pair i lacks
+          for (int i = 0; i < 4; ++i) {
+            const int extra = (p == p0 ? 3 - i : 0) + (p == p1 - 1 ? i : 0);
+            for (int k = 0; k < extra; ++k) umma_commit(pfree_bar((g_lo + i) & (kTsSlots - 1)));
+          }
+          umma_commit(tfull_bar(acc));
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ epilogue + pooling ======================================
+    const int et = threadIdx.x - (1 + kTsBuildW + kTsMmaW) * 32;  // 0..255
+    const int wq = warp & 3, half = (warp - (1 + kTsBuildW + kTsMmaW)) >> 2;  // TMEM lane quarter, channel half
+    const int q = wq * 32 + lane;
+    const float2 *prm = reinterpret_cast<const float2 *>(smem + kTsPrmOff);
+    uint8_t *cring = smem + kTsConvOff;
+    const bool f32_out = a.out_mode == SLQ_OUT_F32;
+    int rc = 0;
+    for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+      int n, j0, j1, p0, p1;
+      unit_rows(a, u, n, j0, j1, p0, p1);
+      for (int p = p0; p < p1; ++p, ++rc) {
+        const int acc = rc & 3;
+        mbar_wait(tfull_bar(acc), (uint32_t)((rc >> 2) & 1));
+        tc_fence_after();
+        uint32_t av[32];
+        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kTsAccCols + half * 32, av);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));  // accumulator is in registers: row rc + 4 may start
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float4 p4 = *reinterpret_cast<const float4 *>(&prm[half * 32 + j]);  // {a0, b0, a1, b1}
+          const float2 r = ffma2(make_float2(__uint_as_float(av[j]), __uint_as_float(av[j + 1])),
+                                 make_float2(p4.x, p4.z), make_float2(p4.y, p4.w));  // u8: in units of the output scale
+          y[j] = r.x; y[j + 1] = r.y;
+        }
+        if (f32_out) {
+          if (q < a.Wc) {
+            float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.out) +
+                                                   (((long long)n * a.Hc + p) * a.Wc + q) * 64 + half * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = make_float4(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f), fmaxf(y[4 * j + 2], 0.f),
+                                 fmaxf(y[4 * j + 3], 0.f));
+          }
+          continue;
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // saturation at 0 is the ReLU
+          pk[j] = epi_pack4<false>(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        uint4 *dst = reinterpret_cast<uint4 *>(cring + (p & (kSfConvRing - 1)) * kSfConvRowBytes + q * 64 + half * 32);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        named_bar_sync(2, kTsEpi);  // conv row p is complete in the ring
+        // pooled row j = max over conv rows 2j-1..2j+1: complete after an odd row or the last row
+        if (!((p & 1) || p == a.Hc - 1)) continue;
+        const int j = p >> 1;
+        if (j < j0) continue;  // the seam row only feeds this unit's first pooled row
+        const int r0 = max(2 * j - 1, 0), r1 = 2 * j, r2 = min(2 * j + 1, a.Hc - 1);
+        const uint8_t *row0 = cring + (r0 & (kSfConvRing - 1)) * kSfConvRowBytes;
+        const uint8_t *row1 = cring + (r1 & (kSfConvRing - 1)) * kSfConvRowBytes;
+        const uint8_t *row2 = cring + (r2 & (kSfConvRing - 1)) * kSfConvRowBytes;
+        uint4 *orow = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) +
+                                                (((long long)n * a.Hp + j) * a.Wp) * 64);
+        uint32_t *rsrow = a.out_rowsum ? a.out_rowsum + ((long long)n * a.Hp + j) * a.Wp : nullptr;
+        for (int base = et & ~31; base < a.Wp * 4; base += kTsEpi) {  // whole warps walk the loop (shuffles below)
+          const int idx = base + lane;
+          const bool live = idx < a.Wp * 4;
+          const int i = idx >> 2, gch = (idx & 3) * 16;
+          uint4 m = make_uint4(0, 0, 0, 0);
+          if (live) {
+            const int c0 = max(2 * i - 1, 0) * 64 + gch, c1 = 2 * i * 64 + gch, c2 = min(2 * i + 1, a.Wc - 1) * 64 + gch;
+            m = *reinterpret_cast<const uint4 *>(row0 + c0);
+            auto mx = [&](const uint8_t *ptr) {
+              const uint4 v = *reinterpret_cast<const uint4 *>(ptr);
+              m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
+            };
+            mx(row0 + c1); mx(row0 + c2);
+            mx(row1 + c0); mx(row1 + c1); mx(row1 + c2);
+            mx(row2 + c0); mx(row2 + c1); mx(row2 + c2);
+            orow[idx] = m;
+          }
+          uint32_t ps = __dp4a(m.x, 0x01010101u, __dp4a(m.y, 0x01010101u, __dp4a(m.z, 0x01010101u, __dp4a(m.w, 0x01010101u, 0u))));
+          ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+          ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+          if (live && rsrow && (idx & 3) == 0) rsrow[i] = ps;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTsTmemCols) : "memory");
+  }
+}
+
 }  // namespace slq
 
 using namespace slq;
@@ -450,6 +811,10 @@ extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace,
     return SLQ_ERR_UNSUPPORTED;
   }
   s->wh = reinterpret_cast<__half *>(workspace);
+  s->use_ts = (W % 16 == 0) ? 1 : 0;
+#if SLQ_DEBUG_TRACE
+  if (getenv("SLQ_STEM_OLD")) s->use_ts = 0;  // A/B timing of the round-1 kernel (debug build only)
+#endif
   const int units_per_img = (s->Hp + kSfUnitRows - 1) / kSfUnitRows;
   s->num_ctas = (int)std::min<long long>((long long)N * units_per_img, sm_count());
   static bool attr_done[kMaxDevices] = {false};
@@ -460,6 +825,12 @@ extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace,
       e = cudaFuncSetAttribute(stem_fused_kernel<SLQ_IN_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(stem_fused_kernel<SLQ_IN_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSfSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stem_ts_kernel<SLQ_IN_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stem_ts_kernel<SLQ_IN_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(stem_ts_kernel<SLQ_IN_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes);
     if (e != cudaSuccess) {
       delete s;
       set_error("slq_stem_create: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -475,7 +846,8 @@ extern "C" void slq_stem_destroy(slq_stem *s) { delete s; }
 
 extern "C" int slq_stem_set_weights(slq_stem *s, const float *w, void *stream) {
   SLQ_CHECK_ARG(s && w, "slq_stem_set_weights: null pointer argument");
-  stem_weights_kernel<<<(64 * kSfK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wh);
+  if (s->use_ts) stem_weights_ts_kernel<<<(64 * kSfK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wh);
+  else stem_weights_kernel<<<(64 * kSfK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wh);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }
@@ -521,7 +893,12 @@ extern "C" int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, c
     a.dbg = 0;
 #endif
   }
-  if (in_kind == SLQ_IN_F32) stem_fused_kernel<SLQ_IN_F32><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
+  if (s->use_ts) {
+    SLQ_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0, "slq_stem_launch: the image must be 16-byte aligned");
+    if (in_kind == SLQ_IN_F32) stem_ts_kernel<SLQ_IN_F32><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(a);
+    else if (in_kind == SLQ_IN_F16) stem_ts_kernel<SLQ_IN_F16><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(a);
+    else stem_ts_kernel<SLQ_IN_U8><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(a);
+  } else if (in_kind == SLQ_IN_F32) stem_fused_kernel<SLQ_IN_F32><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   else if (in_kind == SLQ_IN_F16) stem_fused_kernel<SLQ_IN_F16><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   else stem_fused_kernel<SLQ_IN_U8><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   SLQ_LAUNCH_CHECK();

@@ -17,7 +17,7 @@ L.check(lib.slq_stem_create(N, H, W, ws.data_ptr(), ctypes.byref(h)))
 L.check(lib.slq_stem_set_weights(h, w.data_ptr(), L.current_stream()))
 out = torch.empty(N * 56 * 56 * 64, dtype=torch.uint8, device="cuda")
 scratch = torch.empty(16, device="cuda")
-for dbg in [int(v) for v in os.environ.get("STEM_DBG_LIST", "0,4,5,29").split(",")]:
+for dbg in [int(v) for v in os.environ.get("STEM_DBG_LIST", "0").split(",")]:
     os.environ["SLQ_STEM_DBG"] = str(dbg)
     for _ in range(2):
         L.check(lib.slq_stem_launch(h, x.data_ptr(), a.data_ptr(), b.data_ptr(), sc.data_ptr(), 0, out.data_ptr(), L.OUT_U8, scratch.data_ptr(), None, L.current_stream()))
