@@ -253,9 +253,13 @@ SLQ_API int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, cons
                                void *out, int32_t out_mode, float *f32_scratch, uint32_t *out_rowsum, void *stream);
 
 /* Tail: resnet.py:216-218  adaptive_avg_pool2d((1,1)) + flatten + fc (fp32 weights + bias).
- * x u8 NHWC [N, HW, C] -> logits fp32 [N, O]; pooled is scratch [N, C] fp32.                     */
+ * x u8 NHWC [N, HW, C] -> logits fp32 [N, O].  The fc runs as a split-K GEMM on the tensor cores
+ * (tcgen05.mma kind::tf32, fp32 accumulation; the weights stay the reference's fp32 tensor in HBM).
+ * workspace: slq_tail_workspace_bytes(N, C, O) bytes, 16-byte aligned, caller-owned (pooled activations +
+ * the per-split partial sums, which are added in a fixed order: the result is deterministic).          */
+SLQ_API int64_t slq_tail_workspace_bytes(int32_t N, int32_t C, int32_t O);
 SLQ_API int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C, const float *act_scales,
-                     int32_t in_id, const float *fc_w, const float *fc_b, int32_t O, float *pooled,
+                     int32_t in_id, const float *fc_w, const float *fc_b, int32_t O, float *workspace,
                      float *logits, void *stream);
 
 /* Calibration of the static per-tensor activation scales (the reference never quantises

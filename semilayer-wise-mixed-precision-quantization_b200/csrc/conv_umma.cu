@@ -713,7 +713,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if (OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr && valid) atomicAdd(e.out_rowsum + m, rsum);
       tc_fence_before();
       if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
       mbar_arrive(tempty_bar(tb));  // kTeam arrivals release the accumulator buffer
@@ -730,6 +729,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      // per-pixel channel sum of this tile's u8 outputs -> side tensor of the output activation.  LAST in the
+      // iteration: a fire-and-forget reduction issued before the proxy fence / barrier above would have its
+      // round trip to L2 waited for there, once per tile
+      if (OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr && valid) atomicAdd(e.out_rowsum + m, rsum);
     }
     if (a.tma_out && et == 0) tma_store_wait_all();
     if (kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && et == 0) { a.trace[6 + team] = wepi; a.trace[12 + team] = clock64() - tstart_clk; }

@@ -3,7 +3,6 @@
 //   * SIMT (dp4a) convolution with the same fused epilogue: the on-device cross-check of the
 //     tcgen05 kernel (tests) -- NOT the product path
 //   * stem   (resnet.py:206-209: conv 7x7 s2 + bn + relu + maxpool 3x3 s2), fp32 weights
-//   * tail   (resnet.py:216-218: avgpool + flatten + fc), fp32 weights
 //   * activation-scale calibration helpers (abs-max -> scale, fp32 -> u8/s8)
 #include "conv_common.cuh"
 
@@ -244,104 +243,6 @@ int launch_stem_pool(const float *y, int N, int Hc, int Wc, int Hp, int Wp, cons
 }
 
 // ------------------------------------------------------------------------------------------
-// Tail: global average pool over u8 NHWC + fc
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) avgpool_kernel(const uint8_t *__restrict__ x, int HW, int C,
-                                                      const float *__restrict__ act_scales, int in_id,
-                                                      float *__restrict__ pooled) {
-  const int n = blockIdx.y;
-  const int c4 = blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 channels
-  if (c4 * 4 >= C) return;
-  const uint32_t *p = reinterpret_cast<const uint32_t *>(x + (long long)n * HW * C) + c4;
-  unsigned s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  for (int i = 0; i < HW; ++i) {
-    const uint32_t v = __ldg(p + (long long)i * (C / 4));
-    s0 += v & 255; s1 += (v >> 8) & 255; s2 += (v >> 16) & 255; s3 += v >> 24;
-  }
-  const float k = __fdiv_rn(act_scales[in_id], (float)HW);
-  float4 o = make_float4((float)s0 * k, (float)s1 * k, (float)s2 * k, (float)s3 * k);
-  *reinterpret_cast<float4 *>(pooled + (long long)n * C + c4 * 4) = o;
-}
-
-// logits[n, o] = sum_c pooled[n, c] * fw[o, c] + fb[o]   (fp32 CUDA cores; fc weights stay fp32).
-// CTA = 32 images x 64 outputs, K chunks of 32 staged transposed in smem ([k][n], [k][o]) so the inner
-// loop is 2 LDS.128 + 16 FFMA; the 256 threads are two K-halves of 128 threads (4x4 outputs each)
-// whose partial sums meet in smem at the end (fixed order: deterministic).  Next chunk's global
-// loads are issued before the current chunk's math.
-constexpr int kFcBN = 32, kFcBO = 64, kFcBK = 32;
-
-__global__ void __launch_bounds__(256) fc_kernel(const float *__restrict__ pooled, int N, int C,
-                                                 const float *__restrict__ fw, const float *__restrict__ fb,
-                                                 int O, float *__restrict__ logits) {
-  __shared__ __align__(16) float As[2][kFcBK][kFcBN + 4];
-  __shared__ __align__(16) float Bs[2][kFcBK][kFcBO + 4];
-  const int tid = threadIdx.x;
-  const int kg = tid >> 7;                 // K half of every chunk
-  const int tn = tid & 7, to = (tid >> 3) & 15;
-  const int n0 = blockIdx.y * kFcBN, o0 = blockIdx.x * kFcBO;
-  // loader mapping: one float4 (4 consecutive k) of A and two of B per thread
-  const int lr = tid >> 3, lk = (tid & 7) * 4;  // row 0..31, k offset 0..28
-  const bool a_ok = n0 + lr < N;
-  const bool b0_ok = o0 + lr < O, b1_ok = o0 + 32 + lr < O;
-  const float4 *pa = reinterpret_cast<const float4 *>(pooled + (long long)(n0 + lr) * C + lk);
-  const float4 *pb0 = reinterpret_cast<const float4 *>(fw + (long long)(o0 + lr) * C + lk);
-  const float4 *pb1 = reinterpret_cast<const float4 *>(fw + (long long)(o0 + 32 + lr) * C + lk);
-  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 ra = a_ok ? __ldg(pa) : zero4, rb0 = b0_ok ? __ldg(pb0) : zero4, rb1 = b1_ok ? __ldg(pb1) : zero4;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int chunks = C / kFcBK;
-  for (int ch = 0; ch < chunks; ++ch) {
-    const int buf = ch & 1;
-    As[buf][lk + 0][lr] = ra.x; As[buf][lk + 1][lr] = ra.y; As[buf][lk + 2][lr] = ra.z; As[buf][lk + 3][lr] = ra.w;
-    Bs[buf][lk + 0][lr] = rb0.x; Bs[buf][lk + 1][lr] = rb0.y; Bs[buf][lk + 2][lr] = rb0.z; Bs[buf][lk + 3][lr] = rb0.w;
-    Bs[buf][lk + 0][32 + lr] = rb1.x; Bs[buf][lk + 1][32 + lr] = rb1.y;
-    Bs[buf][lk + 2][32 + lr] = rb1.z; Bs[buf][lk + 3][32 + lr] = rb1.w;
-    __syncthreads();  // one barrier per chunk: the other buffer is only rewritten after the next barrier
-    if (ch + 1 < chunks) {
-      const int adv = (ch + 1) * (kFcBK / 4);
-      ra = a_ok ? __ldg(pa + adv) : zero4;
-      rb0 = b0_ok ? __ldg(pb0 + adv) : zero4;
-      rb1 = b1_ok ? __ldg(pb1 + adv) : zero4;
-    }
-#pragma unroll
-    for (int kk = 0; kk < kFcBK / 2; ++kk) {
-      const int k = kg * (kFcBK / 2) + kk;
-      const float4 a = *reinterpret_cast<const float4 *>(&As[buf][k][tn * 4]);
-      const float4 b = *reinterpret_cast<const float4 *>(&Bs[buf][k][to * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-  }
-  __syncthreads();
-  float *red = &Bs[0][0][0];  // 128 threads x 16 partial sums = 2048 floats <= one Bs buffer
-  if (kg == 1) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) red[(i * 4 + j) * 128 + (tid & 127)] = acc[i][j];
-  }
-  __syncthreads();
-  if (kg == 0) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int n = n0 + tn * 4 + i;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int o = o0 + to * 4 + j;
-        if (n < N && o < O) logits[(long long)n * O + o] = (acc[i][j] + red[(i * 4 + j) * 128 + tid]) + fb[o];
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Calibration helpers
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) absmax_kernel(const float *__restrict__ y, long long n,
@@ -427,22 +328,6 @@ extern "C" int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W,
   stem_conv_kernel<<<grid, 256, 0, st>>>(x, N, H, W, Hc, Wc, w, bn_a, bn_b, scratch);
   SLQ_LAUNCH_CHECK();
   return launch_stem_pool(scratch, N, Hc, Wc, Hp, Wp, act_scales, out_id, out, out_mode, out_rowsum, st);
-}
-
-extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C,
-                                const float *act_scales, int32_t in_id, const float *fc_w,
-                                const float *fc_b, int32_t O, float *pooled, float *logits,
-                                void *stream) {
-  SLQ_CHECK_ARG(x && act_scales && fc_w && fc_b && pooled && logits, "slq_tail_forward: null pointer argument");
-  SLQ_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C % 32 == 0 && O > 0, "slq_tail_forward: bad shape (C must be a multiple of 32)");
-  cudaStream_t st = (cudaStream_t)stream;
-  dim3 g1((unsigned)ceil_div(C / 4, 256), (unsigned)N);
-  avgpool_kernel<<<g1, 256, 0, st>>>(x, HW, C, act_scales, in_id, pooled);
-  SLQ_LAUNCH_CHECK();
-  dim3 g2((unsigned)ceil_div(O, kFcBO), (unsigned)ceil_div(N, kFcBN));
-  fc_kernel<<<g2, 256, 0, st>>>(pooled, N, C, fc_w, fc_b, O, logits);
-  SLQ_LAUNCH_CHECK();
-  return SLQ_OK;
 }
 
 extern "C" int slq_absmax_scale(const float *y, int64_t n, float *act_scales, int32_t id,

@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
         mbar_wait(sfull_bar(s), ph);
         // 1. raw -> fp16, every element once
         const uint8_t *stg = smem + kTsStageOff + s * kTsStageBytes;
-        for (int idx = bt; idx < groups; idx += kTsBuilders) {
+        for (int idx = bt; idx < groups && !(SF_DBG(a) & 1); idx += kTsBuilders) {
           const int r6 = idx / w4, c4 = idx - r6 * w4;
           const int h = 2 * t + (r6 & 1), c = r6 >> 1;
           float f[4] = {0.f, 0.f, 0.f, 0.f};
@@ -633,7 +633,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
         // 3. this thread's 16-byte windows x[c][h][2q-3 .. 2q+4] -> the slab's TMEM columns
         const uint32_t tslab = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTsSlabBase + s * kTsSlotCols;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < 3 && !(SF_DBG(a) & 2); ++k) {
           const int r6 = sub * 3 + k;  // = c * 2 + j
           const uint32_t *src = reinterpret_cast<const uint32_t *>(rb + r6 * kTsRowP + 2 * q);
           tmem_st4(tslab + (r6 >> 1) * 8 + (r6 & 1) * 4, src[0], src[1], src[2], src[3]);
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
         tc_fence_after();
         if (elect_one()) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
+          for (int i = 0; i < 4 && !(SF_DBG(a) & 8); ++i) {
             const uint32_t ta = tmem_u + kTsSlabBase + ((g_lo + i) & (kTsSlots - 1)) * kTsSlotCols;
 #pragma unroll
             for (int c = 0; c < 3; ++c)
@@ -709,6 +709,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
         tmem_ld_wait();
         tc_fence_before();
         mbar_arrive(tempty_bar(acc));  // accumulator is in registers: row rc + 4 may start
+        if (SF_DBG(a) & 4) continue;
         float y[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {

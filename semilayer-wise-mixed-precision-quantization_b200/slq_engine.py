@@ -183,7 +183,8 @@ class Engine:
         self.f32_scratch = torch.empty(max_out, dtype=torch.float32, device=dev)
         self.act_scales = torch.ones(len(self.act), dtype=torch.float32, device=dev)
         self.absmax_tmp = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.pooled = torch.empty((N, self.final_c), dtype=torch.float32, device=dev)
+        self.tail_ws = torch.empty(self.lib.slq_tail_workspace_bytes(N, self.final_c, net.fc.out_features) // 4,
+                                   dtype=torch.float32, device=dev)
         self.logits = torch.empty((N, net.fc.out_features), dtype=torch.float32, device=dev)
         self.stem_w = torch.zeros_like(net.conv1.weight, dtype=torch.float32, device=dev)
         self.stem_a = torch.zeros(64, dtype=torch.float32, device=dev)
@@ -431,8 +432,8 @@ class Engine:
             L.check(lib.slq_conv_launch(op.handle, ctypes.byref(e), st))
         L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
                                      sc, self.final_id, self.fc_w.data_ptr(), self.fc_b.data_ptr(),
-                                     self.logits.shape[1], self.pooled.data_ptr(), self.logits.data_ptr(), st))
-        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 2  # + one memset node
+                                     self.logits.shape[1], self.tail_ws.data_ptr(), self.logits.data_ptr(), st))
+        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 3  # + one memset node
 
     def _zero_rowsums(self, st):
         L.check(self.lib.slq_zero_async(self.rowsum_pool.data_ptr(), self.rowsum_pool.numel() * 4, st))
