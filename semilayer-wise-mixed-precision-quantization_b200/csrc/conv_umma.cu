@@ -40,7 +40,6 @@
 namespace slq {
 
 constexpr int kThreads = 640;   // 20 warps: 96 registers per thread (the epilogue needs them)
-constexpr int kMmaWarp1 = 3;    // second MMA-issuing warp (the first is warp 1)
 constexpr int kTeam = 256;  // threads of one epilogue team
 constexpr int kOutTileBytes = kTileM * 128;  // u8 output / residual staging tile (128 rows x <=128 B)
 

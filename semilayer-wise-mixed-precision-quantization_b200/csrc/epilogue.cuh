@@ -77,6 +77,9 @@ __device__ __forceinline__ float epi_add_res(float y, uint32_t res_byte, bool re
 // two independent fused multiply-adds in ONE instruction (sm_100 FFMA2): d = a * b + c per component, each
 // rounded once, i.e. bit-identical to two __fmaf_rn calls
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+#ifdef SLQ_NO_FFMA2  // A/B timing only (tools/gpu_*.sh build a variant library with it)
+  return make_float2(__fmaf_rn(a.x, b.x, c.x), __fmaf_rn(a.y, b.y, c.y));
+#endif
   uint64_t ra, rb, rc, rd;
   asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
   asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));

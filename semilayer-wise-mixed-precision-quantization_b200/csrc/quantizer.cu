@@ -487,7 +487,8 @@ __device__ __forceinline__ void quantize_job(const slq_qjob &jb, bool active, in
   }
   if (GROUP <= 32) {
     const unsigned lane = threadIdx.x & 31;
-    const unsigned gmask = GROUP == 32 ? 0xffffffffu : (((1u << GROUP) - 1u) << (lane & ~(unsigned)(GROUP - 1)));
+    constexpr unsigned kOnes = GROUP < 32 ? ((1u << (GROUP & 31)) - 1u) : 0xffffffffu;  // GROUP lanes
+    const unsigned gmask = kOnes << (lane & ~(unsigned)((GROUP - 1) & 31));
     bad = (__ballot_sync(0xffffffffu, bad) & gmask) != 0;
   } else {
     bad = __syncthreads_or(bad);

@@ -493,7 +493,7 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
 }
 
 template <int IN>
-__global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a) {
+__global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_constant__ CUtensorMap tmX, const StemArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -524,6 +524,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
     fence_barrier_init();
   }
   if (warp == 0) {
+    if (lane == 0) prefetch_tmap(&tmX);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32((const void *)tmem_slot)),
                  "r"(kTsTmemCols)
@@ -555,29 +556,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
   // pairs g_lo .. g_lo + 3 with g_lo = rc + 3 u.
   if (warp == 0) {
     // ================================ producer: raw rows -> staging ring ======================
+    // ONE tensor load per pair: box {W, 2 rows, 3 channels} of the image viewed as [3N planes][H][W]; rows
+    // above / below the image are zero-filled by the TMA unit (the conv's padding).  (Six 1-D bulk copies
+    // per pair cost the issuing thread ~1800 cycles -- more than everything else in the kernel.)
     int g = 0;
+    const uint32_t pair_bytes = (uint32_t)(6 * row_bytes);
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
-      const uint8_t *xn = reinterpret_cast<const uint8_t *>(a.x) + (long long)n * 3 * a.H * row_bytes;
       for (int t = p0 - 2; t <= p1; ++t, ++g) {
         const int s = g & (kTsSlots - 1);
         mbar_wait(sempty_bar(s), (uint32_t)(((g >> 3) & 1) ^ 1));
         if (elect_one()) {
-          const int h0 = 2 * t;
-          const int live = (h0 >= 0 && h0 < a.H ? 1 : 0) + (h0 + 1 >= 0 && h0 + 1 < a.H ? 1 : 0);
-          if (live == 0) {
-            mbar_arrive(sfull_bar(s));  // a pair of padding rows: nothing to copy
-          } else {
-            mbar_expect_tx(sfull_bar(s), (uint32_t)(3 * live * row_bytes));
-            for (int c = 0; c < 3; ++c)
-              for (int j = 0; j < 2; ++j) {
-                const int h = h0 + j;
-                if (h < 0 || h >= a.H) continue;
-                bulk_copy_g2s(smem_base + kTsStageOff + s * kTsStageBytes + (c * 2 + j) * kTsMaxRowBytes,
-                              xn + ((long long)c * a.H + h) * row_bytes, (uint32_t)row_bytes, sfull_bar(s));
-              }
-          }
+          mbar_expect_tx(sfull_bar(s), pair_bytes);
+          tma_load_3d(smem_base + kTsStageOff + s * kTsStageBytes, &tmX, sfull_bar(s), 0, 2 * t, 3 * n);
         }
         __syncwarp();
       }
@@ -589,7 +581,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
     const int sub = (warp - 1) >> 2;                 // which three of the six (c, j) rows of a pair it writes
     const int q = quarter * 32 + lane;               // output column == TMEM lane
     __half *rowbuf = reinterpret_cast<__half *>(smem + kTsRowBufOff);
-    const int w4 = a.W >> 2, groups = 6 * w4;        // 4-element groups of the six rows
+    const int w4 = a.W >> 2;                         // 4-element groups per row (<= 64)
     int g = 0;
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
@@ -599,26 +591,28 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
         const uint32_t ph = (uint32_t)((g >> 3) & 1);
         __half *rb = rowbuf + (g & 1) * 6 * kTsRowP;
         mbar_wait(sfull_bar(s), ph);
-        // 1. raw -> fp16, every element once
+        // 1. raw -> fp16, every element once: thread = (row r6 of the six, 4-element group c4); two passes
         const uint8_t *stg = smem + kTsStageOff + s * kTsStageBytes;
-        for (int idx = bt; idx < groups && !(SF_DBG(a) & 1); idx += kTsBuilders) {
-          const int r6 = idx / w4, c4 = idx - r6 * w4;
-          const int h = 2 * t + (r6 & 1), c = r6 >> 1;
-          float f[4] = {0.f, 0.f, 0.f, 0.f};
-          if (h >= 0 && h < a.H) {
-            const uint8_t *src = stg + r6 * kTsMaxRowBytes + c4 * 4 * ESZ;
-            if (IN == SLQ_IN_F32) {
-              const float4 v = *reinterpret_cast<const float4 *>(src);
-              f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
-            } else if (IN == SLQ_IN_F16) {
-              const uint2 v = *reinterpret_cast<const uint2 *>(src);
-              f[0] = stem_pixel<IN>(v.x & 0xffffu, 0.f, 1.f); f[1] = stem_pixel<IN>(v.x >> 16, 0.f, 1.f);
-              f[2] = stem_pixel<IN>(v.y & 0xffffu, 0.f, 1.f); f[3] = stem_pixel<IN>(v.y >> 16, 0.f, 1.f);
-            } else {
-              const uint32_t v = *reinterpret_cast<const uint32_t *>(src);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) f[e] = stem_pixel<IN>((v >> (8 * e)) & 255u, a.nmean[c], a.nstd[c]);
-            }
+        for (int pass = 0; pass < 2; ++pass) {
+          const int r6 = pass * 4 + (bt >> 6), c4 = bt & 63;
+          if (r6 >= 6 || c4 >= w4 || (SF_DBG(a) & 1)) continue;
+          const int c = r6 >> 1;
+          float f[4];
+          const uint8_t *src = stg + r6 * row_bytes + c4 * 4 * ESZ;  // rows outside the image arrive as zeros
+          if (IN == SLQ_IN_F32) {
+            const float4 v = *reinterpret_cast<const float4 *>(src);
+            f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+          } else if (IN == SLQ_IN_F16) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(src);
+            f[0] = stem_pixel<IN>(v.x & 0xffffu, 0.f, 1.f); f[1] = stem_pixel<IN>(v.x >> 16, 0.f, 1.f);
+            f[2] = stem_pixel<IN>(v.y & 0xffffu, 0.f, 1.f); f[3] = stem_pixel<IN>(v.y >> 16, 0.f, 1.f);
+          } else {
+            const uint32_t v = *reinterpret_cast<const uint32_t *>(src);
+            const int h = 2 * t + (r6 & 1);
+            const bool inside = h >= 0 && h < a.H;  // a zero BYTE is a pixel value: padding rows must become 0.0
+#pragma unroll
+            for (int e = 0; e < 4; ++e) f[e] = inside ? stem_pixel<IN>((v >> (8 * e)) & 255u, a.nmean[c], a.nstd[c]) : 0.f;
           }
           __half *dst = rb + r6 * kTsRowP + 3 + 4 * c4;  // 2-byte aligned (cc = w + 3)
           dst[0] = __float2half_rn(f[0]);
@@ -696,6 +690,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
     const float2 *prm = reinterpret_cast<const float2 *>(smem + kTsPrmOff);
     uint8_t *cring = smem + kTsConvOff;
     const bool f32_out = a.out_mode == SLQ_OUT_F32;
+    uint32_t vm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // running vertical maximum of the pooling window (packed u8)
     int rc = 0;
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
@@ -733,36 +728,47 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const StemArgs a
 #pragma unroll
         for (int j = 0; j < 8; ++j)  // saturation at 0 is the ReLU
           pk[j] = epi_pack4<false>(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
-        uint4 *dst = reinterpret_cast<uint4 *>(cring + (p & (kSfConvRing - 1)) * kSfConvRowBytes + q * 64 + half * 32);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        named_bar_sync(2, kTsEpi);  // conv row p is complete in the ring
-        // pooled row j = max over conv rows 2j-1..2j+1: complete after an odd row or the last row
-        if (!((p & 1) || p == a.Hc - 1)) continue;
-        const int j = p >> 1;
-        if (j < j0) continue;  // the seam row only feeds this unit's first pooled row
-        const int r0 = max(2 * j - 1, 0), r1 = 2 * j, r2 = min(2 * j + 1, a.Hc - 1);
-        const uint8_t *row0 = cring + (r0 & (kSfConvRing - 1)) * kSfConvRowBytes;
-        const uint8_t *row1 = cring + (r1 & (kSfConvRing - 1)) * kSfConvRowBytes;
-        const uint8_t *row2 = cring + (r2 & (kSfConvRing - 1)) * kSfConvRowBytes;
+        // 3x3 / stride-2 max-pool, separable: the VERTICAL maximum over conv rows 2j-1, 2j, 2j+1 is kept in
+        // registers (this thread always owns the same column and channels), so only every second row goes to
+        // shared memory and costs a barrier; the horizontal maximum then reads 3 pixels instead of 9
+        if (p == p0) {  // the first conv row of a unit opens a window (and closes none)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vm[j] = pk[j];
+        } else {        // rows 2j and 2j+1 extend the window that row 2j-1 opened
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vm[j] = __vmaxu4(vm[j], pk[j]);
+        }
+        const int jrow = p >> 1;
+        // pooled row jrow is complete with an odd conv row (or the last one); the seam row 2 j0 - 1 at the start
+        // of a unit belongs to the previous unit's pooled row and only opens this unit's first window
+        const bool emit = ((p & 1) || p == a.Hc - 1) && jrow >= j0 && p != p0;
+        if (emit) {
+          uint4 *dst = reinterpret_cast<uint4 *>(cring + (jrow & 1) * kSfConvRowBytes + q * 64 + half * 32);
+          dst[0] = make_uint4(vm[0], vm[1], vm[2], vm[3]);
+          dst[1] = make_uint4(vm[4], vm[5], vm[6], vm[7]);
+        }
+        if (p & 1) {  // an odd row also opens the next window
+#pragma unroll
+          for (int j = 0; j < 8; ++j) vm[j] = pk[j];
+        }
+        if (!emit) continue;
+        named_bar_sync(2, kTsEpi);  // the vertically pooled row is complete in its slot (2 slots alternate)
+        const uint8_t *vrow = cring + (jrow & 1) * kSfConvRowBytes;
         uint4 *orow = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) +
-                                                (((long long)n * a.Hp + j) * a.Wp) * 64);
-        uint32_t *rsrow = a.out_rowsum ? a.out_rowsum + ((long long)n * a.Hp + j) * a.Wp : nullptr;
+                                                (((long long)n * a.Hp + jrow) * a.Wp) * 64);
+        uint32_t *rsrow = a.out_rowsum ? a.out_rowsum + ((long long)n * a.Hp + jrow) * a.Wp : nullptr;
         for (int base = et & ~31; base < a.Wp * 4; base += kTsEpi) {  // whole warps walk the loop (shuffles below)
           const int idx = base + lane;
           const bool live = idx < a.Wp * 4;
           const int i = idx >> 2, gch = (idx & 3) * 16;
           uint4 m = make_uint4(0, 0, 0, 0);
           if (live) {
+            // clamped columns: a duplicated column does not change a maximum
             const int c0 = max(2 * i - 1, 0) * 64 + gch, c1 = 2 * i * 64 + gch, c2 = min(2 * i + 1, a.Wc - 1) * 64 + gch;
-            m = *reinterpret_cast<const uint4 *>(row0 + c0);
-            auto mx = [&](const uint8_t *ptr) {
-              const uint4 v = *reinterpret_cast<const uint4 *>(ptr);
-              m.x = __vmaxu4(m.x, v.x); m.y = __vmaxu4(m.y, v.y); m.z = __vmaxu4(m.z, v.z); m.w = __vmaxu4(m.w, v.w);
-            };
-            mx(row0 + c1); mx(row0 + c2);
-            mx(row1 + c0); mx(row1 + c1); mx(row1 + c2);
-            mx(row2 + c0); mx(row2 + c1); mx(row2 + c2);
+            m = *reinterpret_cast<const uint4 *>(vrow + c0);
+            const uint4 v1 = *reinterpret_cast<const uint4 *>(vrow + c1), v2 = *reinterpret_cast<const uint4 *>(vrow + c2);
+            m.x = __vmaxu4(__vmaxu4(m.x, v1.x), v2.x); m.y = __vmaxu4(__vmaxu4(m.y, v1.y), v2.y);
+            m.z = __vmaxu4(__vmaxu4(m.z, v1.z), v2.z); m.w = __vmaxu4(__vmaxu4(m.w, v1.w), v2.w);
             orow[idx] = m;
           }
           uint32_t ps = __dp4a(m.x, 0x01010101u, __dp4a(m.y, 0x01010101u, __dp4a(m.z, 0x01010101u, __dp4a(m.w, 0x01010101u, 0u))));
@@ -896,9 +902,35 @@ extern "C" int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, c
   }
   if (s->use_ts) {
     SLQ_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0, "slq_stem_launch: the image must be 16-byte aligned");
-    if (in_kind == SLQ_IN_F32) stem_ts_kernel<SLQ_IN_F32><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(a);
-    else if (in_kind == SLQ_IN_F16) stem_ts_kernel<SLQ_IN_F16><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(a);
-    else stem_ts_kernel<SLQ_IN_U8><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(a);
+    // the image as a 3-D tensor [3N planes][H][W]; one box = {W, 2 rows, 3 channels} = one input-row pair
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                      const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn enc = nullptr;
+    if (!enc) {
+      void *fp = nullptr;
+      cudaDriverEntryPointQueryResult qr;
+      SLQ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qr));
+      SLQ_CHECK_ARG(qr == cudaDriverEntryPointSuccess && fp, "cuTensorMapEncodeTiled not available from the driver");
+      enc = (EncodeTiledFn)fp;
+    }
+    const int esz = in_kind == SLQ_IN_F32 ? 4 : (in_kind == SLQ_IN_F16 ? 2 : 1);
+    CUtensorMap tmX;
+    cuuint64_t dims[3] = {(cuuint64_t)s->W, (cuuint64_t)s->H, (cuuint64_t)3 * s->N};
+    cuuint64_t strides[2] = {(cuuint64_t)s->W * esz, (cuuint64_t)s->H * s->W * esz};
+    cuuint32_t box[3] = {(cuuint32_t)s->W, 2, 3};
+    cuuint32_t es[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = in_kind == SLQ_IN_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : (in_kind == SLQ_IN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+    const CUresult r = enc(&tmX, dt, 3, const_cast<void *>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(stem image) failed: CUresult %d", (int)r);
+      return SLQ_ERR_CUDA;
+    }
+    if (in_kind == SLQ_IN_F32) stem_ts_kernel<SLQ_IN_F32><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(tmX, a);
+    else if (in_kind == SLQ_IN_F16) stem_ts_kernel<SLQ_IN_F16><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(tmX, a);
+    else stem_ts_kernel<SLQ_IN_U8><<<s->num_ctas, kTsThreads, kTsSmemBytes, st>>>(tmX, a);
   } else if (in_kind == SLQ_IN_F32) stem_fused_kernel<SLQ_IN_F32><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   else if (in_kind == SLQ_IN_F16) stem_fused_kernel<SLQ_IN_F16><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);
   else stem_fused_kernel<SLQ_IN_U8><<<s->num_ctas, kSfThreads, kSfSmemBytes, st>>>(a);

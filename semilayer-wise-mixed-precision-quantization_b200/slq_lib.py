@@ -86,6 +86,8 @@ def lib():
         if os.environ.get("SLQ_DEBUG_LIB") == "1":
             import slq_build
             LIB_PATH = slq_build.build(debug=True)
+        elif os.environ.get("SLQ_LIB_VARIANT"):  # developer tools: an A/B build of the same sources (tools/layer_time.py)
+            LIB_PATH = os.path.join(HERE, "libslq_b200_%s.so" % os.environ["SLQ_LIB_VARIANT"])
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 "libslq_b200.so is missing (%s). Build it with `python slq_build.py`; this package "
