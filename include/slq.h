@@ -254,12 +254,16 @@ SLQ_API int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, cons
 
 /* Tail: resnet.py:216-218  adaptive_avg_pool2d((1,1)) + flatten + fc (fp32 weights + bias).
  * x u8 NHWC [N, HW, C] -> logits fp32 [N, O].  The fc runs as a split-K GEMM on the tensor cores
- * (tcgen05.mma kind::tf32, fp32 accumulation; the weights stay the reference's fp32 tensor in HBM).
- * workspace: slq_tail_workspace_bytes(N, C, O) bytes, 16-byte aligned, caller-owned (pooled activations +
- * the per-split partial sums, which are added in a fixed order: the result is deterministic).          */
+ * (tcgen05.mma kind::tf32, fp32 accumulation).  A TF32 operand carries 10 significand bits, so both operands
+ * are split into two TF32 terms (x = x_hi + x_lo, exact) and three products are accumulated
+ * (lo*hi + hi*lo + hi*hi): fp32-class accuracy for weights the reference keeps in fp32.
+ *   slq_tail_split_weights: fc_w fp32 [O, C] -> fc_w_split fp32 [2][O][C] ({hi, lo} planes), once per weight change
+ *   workspace: slq_tail_workspace_bytes(N, C, O) bytes, 16-byte aligned, caller-owned (pooled {hi, lo} +
+ *   the per-split partial sums, which are added in a fixed order: the result is deterministic).          */
 SLQ_API int64_t slq_tail_workspace_bytes(int32_t N, int32_t C, int32_t O);
+SLQ_API int slq_tail_split_weights(const float *fc_w, int32_t O, int32_t C, float *fc_w_split, void *stream);
 SLQ_API int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C, const float *act_scales,
-                     int32_t in_id, const float *fc_w, const float *fc_b, int32_t O, float *workspace,
+                     int32_t in_id, const float *fc_w_split, const float *fc_b, int32_t O, float *workspace,
                      float *logits, void *stream);
 
 /* Calibration of the static per-tensor activation scales (the reference never quantises

@@ -9,9 +9,12 @@
 //                       256 x 1000 x 2048 problem (a single pass over K on 16 CTAs would be bound by one SM's
 //                       L2 path)
 //   fc_reduce_kernel    logits[n][o] = (sum over splits, FIXED order) + bias[o]
-// Round 1 ran this GEMM on the CUDA cores (55 us of a 2.3 ms step).  Operands pass through the tensor core as
-// TF32 (10-bit significand: ~3e-4 relative, an order of magnitude below the u8 activation quantisation noise
-// of the logits); accumulation, bias and the reduction over the splits are fp32.
+// Round 1 ran this GEMM on the CUDA cores (55 us of a 2.3 ms step).  A TF32 operand carries a 10-bit significand,
+// so BOTH operands are split into two TF32 terms, x = x_hi + x_lo with x_hi = x truncated to TF32 and x_lo the
+// exact remainder, and the product is taken as  a_lo*w_hi + a_hi*w_lo + a_hi*w_hi  (three passes over K into the
+// same fp32 accumulator; the dropped a_lo*w_lo term is ~2^-20 relative): fp32-class accuracy for weights the
+// reference keeps in fp32, at three times a cost that is small to begin with.  Bias and the reduction over the
+// splits are fp32.
 #include <algorithm>
 
 #include "conv_common.cuh"
@@ -19,12 +22,25 @@
 
 namespace slq {
 
+// x truncated to TF32 (sign, 8-bit exponent, 10-bit significand): exactly representable, so the tensor core adds no
+// rounding of its own; x - tf32_hi(x) is exact in fp32
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// fc weights -> {hi, lo} planes: w2[0][i] = tf32_hi(w[i]), w2[1][i] = w[i] - w2[0][i]
+__global__ void __launch_bounds__(256) fc_split_kernel(const float *__restrict__ w, long long n, float *__restrict__ w2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = w[i], h = tf32_hi(v);
+    w2[i] = h;
+    w2[n + i] = __fsub_rn(v, h);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // global average pool: one CTA per image, one thread per 16 channels (16-byte loads)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) avgpool_v2_kernel(const uint8_t *__restrict__ x, int HW, int C,
                                                          const float *__restrict__ act_scales, int in_id,
-                                                         float *__restrict__ pooled) {
+                                                         float *__restrict__ pooled_hi, float *__restrict__ pooled_lo) {
   const int n = blockIdx.x;
   const float k = __fdiv_rn(act_scales[in_id], (float)HW);
   for (int c16 = threadIdx.x; c16 * 16 < C; c16 += blockDim.x) {
@@ -42,10 +58,19 @@ __global__ void __launch_bounds__(128) avgpool_v2_kernel(const uint8_t *__restri
         s[4 * q + 2] += (w[q] >> 16) & 255; s[4 * q + 3] += w[q] >> 24;
       }
     }
-    float4 *o = reinterpret_cast<float4 *>(pooled + (long long)n * C + c16 * 16);
+    float4 *oh = reinterpret_cast<float4 *>(pooled_hi + (long long)n * C + c16 * 16);
+    float4 *ol = reinterpret_cast<float4 *>(pooled_lo + (long long)n * C + c16 * 16);
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      o[q] = make_float4((float)s[4 * q] * k, (float)s[4 * q + 1] * k, (float)s[4 * q + 2] * k, (float)s[4 * q + 3] * k);
+    for (int q = 0; q < 4; ++q) {
+      float v[4], h[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[e] = __fmul_rn((float)s[4 * q + e], k);
+        h[e] = tf32_hi(v[e]);
+      }
+      oh[q] = make_float4(h[0], h[1], h[2], h[3]);
+      ol[q] = make_float4(__fsub_rn(v[0], h[0]), __fsub_rn(v[1], h[1]), __fsub_rn(v[2], h[2]), __fsub_rn(v[3], h[3]));
+    }
   }
 }
 
@@ -67,8 +92,10 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       : "memory");
 }
 
-__global__ void __launch_bounds__(kFcThreads, 1) fc_umma_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                const __grid_constant__ CUtensorMap tmB, int N, int O,
+__global__ void __launch_bounds__(kFcThreads, 1) fc_umma_kernel(const __grid_constant__ CUtensorMap tmAhi,
+                                                                const __grid_constant__ CUtensorMap tmAlo,
+                                                                const __grid_constant__ CUtensorMap tmBhi,
+                                                                const __grid_constant__ CUtensorMap tmBlo, int N, int O,
                                                                 int kb_per_split, float *__restrict__ partial) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -81,8 +108,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_umma_kernel(const __grid_con
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
   if (threadIdx.x == 0) {
-    prefetch_tmap(&tmA);
-    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmAhi);
+    prefetch_tmap(&tmAlo);
+    prefetch_tmap(&tmBhi);
+    prefetch_tmap(&tmBlo);
     for (int s = 0; s < kFcStages; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
@@ -102,22 +131,24 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_umma_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int kb0 = split * kb_per_split;
+  const int steps = 3 * kb_per_split;  // three passes over this CTA's K range: lo*hi, hi*lo, hi*hi
   if (warp == 0) {
-    for (int i = 0; i < kb_per_split; ++i) {
+    for (int i = 0; i < steps; ++i) {
       const int s = i % kFcStages;
+      const int seg = i / kb_per_split, kb = kb0 + (i - seg * kb_per_split);
       mbar_wait(empty_bar(s), (uint32_t)(((i / kFcStages) & 1) ^ 1));
       if (elect_one()) {
         const uint32_t sa = smem_base + s * 2 * kFcTileBytes;
         mbar_expect_tx(full_bar(s), 2 * kFcTileBytes);  // rows past N / O are zero-filled by the TMA and still counted
-        tma_load_2d(sa, &tmA, full_bar(s), (kb0 + i) * 32, m_tile * 128);
-        tma_load_2d(sa + kFcTileBytes, &tmB, full_bar(s), (kb0 + i) * 32, n_tile * 128);
+        tma_load_2d(sa, seg == 0 ? &tmAlo : &tmAhi, full_bar(s), kb * 32, m_tile * 128);
+        tma_load_2d(sa + kFcTileBytes, seg == 1 ? &tmBlo : &tmBhi, full_bar(s), kb * 32, n_tile * 128);
       }
       __syncwarp();
     }
   } else if (warp == 1) {
     // instruction descriptor: D = f32, A = B = tf32 (K-major), M = 128, N = 128
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    for (int i = 0; i < kb_per_split; ++i) {
+    for (int i = 0; i < steps; ++i) {
       const int s = i % kFcStages;
       mbar_wait(full_bar(s), (uint32_t)((i / kFcStages) & 1));
       tc_fence_after();
@@ -128,7 +159,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) fc_umma_kernel(const __grid_con
         for (int k = 0; k < 4; ++k)  // UMMA_K = 8 tf32 = 32 bytes
           umma_tf32(tmem_base, da + 2 * k, db + 2 * k, idesc, (uint32_t)((i | k) != 0));
         umma_commit(empty_bar(s));
-        if (i == kb_per_split - 1) umma_commit(tfull_bar);
+        if (i == steps - 1) umma_commit(tfull_bar);
       }
       __syncwarp();
     }
@@ -220,25 +251,36 @@ using namespace slq;
 
 extern "C" int64_t slq_tail_workspace_bytes(int32_t N, int32_t C, int32_t O) {
   if (N <= 0 || C <= 0 || O <= 0) return -1;
-  return ((int64_t)N * C + (int64_t)fc_splits(C) * N * O) * 4;
+  return (2 * (int64_t)N * C + (int64_t)fc_splits(C) * N * O) * 4;
+}
+
+extern "C" int slq_tail_split_weights(const float *fc_w, int32_t O, int32_t C, float *fc_w_split, void *stream) {
+  SLQ_CHECK_ARG(fc_w && fc_w_split && O > 0 && C > 0, "slq_tail_split_weights: bad argument");
+  const long long n = (long long)O * C;
+  fc_split_kernel<<<(unsigned)std::min<long long>(ceil_div(n, 256), (long long)sm_count() * 8), 256, 0, (cudaStream_t)stream>>>(
+      fc_w, n, fc_w_split);
+  SLQ_LAUNCH_CHECK();
+  return SLQ_OK;
 }
 
 extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C, const float *act_scales,
-                                int32_t in_id, const float *fc_w, const float *fc_b, int32_t O, float *workspace,
+                                int32_t in_id, const float *fc_w_split, const float *fc_b, int32_t O, float *workspace,
                                 float *logits, void *stream) {
+  const float *fc_w = fc_w_split;
   SLQ_CHECK_ARG(x && act_scales && fc_w && fc_b && workspace && logits, "slq_tail_forward: null pointer argument");
   SLQ_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C % 32 == 0 && O > 0, "slq_tail_forward: bad shape (C must be a multiple of 32)");
   SLQ_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(fc_w) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(workspace) % 16 == 0,
                 "slq_tail_forward: x, fc_w and workspace must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  float *pooled = workspace, *partial = workspace + (int64_t)N * C;
-  avgpool_v2_kernel<<<N, 128, 0, st>>>(x, HW, C, act_scales, in_id, pooled);
+  float *pooled_hi = workspace, *pooled_lo = workspace + (int64_t)N * C, *partial = workspace + 2 * (int64_t)N * C;
+  avgpool_v2_kernel<<<N, 128, 0, st>>>(x, HW, C, act_scales, in_id, pooled_hi, pooled_lo);
   SLQ_LAUNCH_CHECK();
-  CUtensorMap tmA, tmB;
-  int rc = encode_f32_rows(&tmA, pooled, N, C);
-  if (rc != SLQ_OK) return rc;
-  rc = encode_f32_rows(&tmB, fc_w, O, C);
+  CUtensorMap tmAhi, tmAlo, tmBhi, tmBlo;
+  int rc = encode_f32_rows(&tmAhi, pooled_hi, N, C);
+  if (rc == SLQ_OK) rc = encode_f32_rows(&tmAlo, pooled_lo, N, C);
+  if (rc == SLQ_OK) rc = encode_f32_rows(&tmBhi, fc_w, O, C);
+  if (rc == SLQ_OK) rc = encode_f32_rows(&tmBlo, fc_w + (int64_t)O * C, O, C);
   if (rc != SLQ_OK) return rc;
   static bool attr_done[kMaxDevices] = {false};
   const int dev = current_device();
@@ -248,7 +290,7 @@ extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t
   }
   const int splits = fc_splits(C);
   dim3 grid((unsigned)ceil_div(O, 128), (unsigned)ceil_div(N, 128), (unsigned)splits);
-  fc_umma_kernel<<<grid, kFcThreads, kFcSmemBytes, st>>>(tmA, tmB, N, O, C / 32 / splits, partial);
+  fc_umma_kernel<<<grid, kFcThreads, kFcSmemBytes, st>>>(tmAhi, tmAlo, tmBhi, tmBlo, N, O, C / 32 / splits, partial);
   SLQ_LAUNCH_CHECK();
   const long long total = (long long)N * O;
   fc_reduce_kernel<<<(unsigned)std::min<long long>(ceil_div(total, 256), (long long)sm_count() * 8), 256, 0, st>>>(

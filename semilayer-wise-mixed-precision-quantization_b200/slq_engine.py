@@ -190,6 +190,7 @@ class Engine:
         self.stem_a = torch.zeros(64, dtype=torch.float32, device=dev)
         self.stem_b = torch.zeros(64, dtype=torch.float32, device=dev)
         self.fc_w = torch.zeros_like(net.fc.weight, dtype=torch.float32, device=dev)
+        self.fc_w_split = torch.zeros((2,) + tuple(net.fc.weight.shape), dtype=torch.float32, device=dev)  # {hi, lo} TF32 terms
         self.fc_b = torch.zeros_like(net.fc.bias, dtype=torch.float32, device=dev)
         self.ends_sig = None
         self.weights_version = 0   # bumped by every sync_weights() that changed something
@@ -302,6 +303,8 @@ class Engine:
                 self.stem_a.copy_(a)
                 self.stem_b.copy_(b)
                 self.fc_w.copy_(self.net.fc.weight.detach())
+                L.check(lib.slq_tail_split_weights(self.fc_w.data_ptr(), self.fc_w.shape[0], self.fc_w.shape[1],
+                                                   self.fc_w_split.data_ptr(), stream))
                 self.fc_b.copy_(self.net.fc.bias.detach())
                 self.ends_sig = ends_sig
         self.weights_version += 1
@@ -431,7 +434,7 @@ class Engine:
             e = self._epilogue(op, mode, self.act[op.out_id].data_ptr())
             L.check(lib.slq_conv_launch(op.handle, ctypes.byref(e), st))
         L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
-                                     sc, self.final_id, self.fc_w.data_ptr(), self.fc_b.data_ptr(),
+                                     sc, self.final_id, self.fc_w_split.data_ptr(), self.fc_b.data_ptr(),
                                      self.logits.shape[1], self.tail_ws.data_ptr(), self.logits.data_ptr(), st))
         self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 3  # + one memset node
 

@@ -64,6 +64,7 @@ SIGNATURES = {
     "slq_stem_launch": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "slq_stem_launch_in": (ctypes.c_int, [_vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _vp]),
     "slq_tail_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "slq_tail_split_weights": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp]),
     "slq_tail_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp]),
     "slq_absmax_scale": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
     "slq_quantize_act": (ctypes.c_int, [_vp, _i64, _vp, _i32, _i32, _vp, _vp]),
