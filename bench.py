@@ -264,6 +264,8 @@ def main():
     ap.add_argument("--no-agree", action="store_true", help="skip the fp32 agreement check (torch kernels)")
     ap.add_argument("--simt", action="store_true", help="run the dp4a checker kernels instead (debug)")
     ap.add_argument("--layers", default="", help="write the per-layer CUDA-event table to this file")
+    ap.add_argument("--no-packed-b", action="store_true",
+                    help="A/B: resident-weight layers take u8 weight tiles through TMA instead of packed codes unpacked in smem")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -342,7 +344,7 @@ def main():
     x = torch.randn(B, 3, 224, 224, generator=g, device=dev)
     x_host = x.cpu().pin_memory()
     impl = L.IMPL_SIMT if args.simt else L.IMPL_UMMA
-    eng = net.slq_engine(x, impl=impl)
+    eng = net.slq_engine(x, impl=impl, packed_b=not args.no_packed_b)
     eng.refresh_weights()
     eng.calibrate(x)
     eng.epoch = resnet.WEIGHT_EPOCH[0]
@@ -571,6 +573,8 @@ def main():
                                "synthetic 224x224, random-init" % (args.arch, int((table[:, 2] == 4).sum()), len(table), B),
                    "batch_per_gpu": B, "global_batch": B * world, "parallelism": "dp%d" % world,
                    "cuda_graph": use_graph, "kernels": "simt-checker" if args.simt else "tcgen05",
+                   "weights": "resident-weight layers fetch PACKED codes (4-bit rows two per byte) and unpack them in shared "
+                              "memory; K-heavy layers stream u8 tiles" if not args.no_packed_b else "u8 tiles everywhere (A/B)",
                    "l2": "per-step working set (u8 activations ~%.1f GB) >> 126 MB L2; no flush needed" %
                          (sum(a.numel() for a in eng.act) / 1e9),
                    "activation_quant": "static per-tensor u8 (calibrated on one batch)"},

@@ -174,6 +174,28 @@ SLQ_API int slq_build_gemm_weights(const slq_conv_desc *d, const uint8_t *codes,
                            const int32_t *bit, uint8_t *wg, void *stream);
 
 SLQ_API int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const uint8_t *wg, slq_conv **out);
+
+/* PACKED weights, unpacked to int8 in shared memory (BASELINE north_star).
+ * Layers whose whole n-tile of weights stays resident in shared memory (the 1x1 convs up to K = 512 and the
+ * 3x3 64->64 convs of ResNet-50) can take their B operand as the packed store itself: per n-tile and K block,
+ * the rows' codes back to back -- rows of <= 4 bits two codes per byte (low nibble = even k), wider rows one code
+ * per byte -- fetched with one bulk copy per K block and expanded in place by the epilogue warps before the first MMA.
+ *   slq_conv_tiling          the tiling the kernel uses for this layer: columns (rows of B) per n-tile, n-tiles,
+ *                            codes of K per K block, K blocks, and whether the weights are resident (packable)
+ *   layout (computed by the caller from the per-channel bit-widths):
+ *     row_offsets[t][r]  (uint16, r = 0..bn_cols)  byte offset of row r inside one (n-tile t, K block) segment;
+ *                        a row takes k_block/2 bytes (bit <= 4) or k_block bytes; rows past Cout count as 4-bit
+ *     seg_bytes[t] = row_offsets[t][bn_cols];  tile_base[t] = sum over earlier tiles of num_kb * seg_bytes
+ *   slq_build_packed_gemm_weights   fills wgp from the per-row packed store (slq_quantize_rows / slq_encode_rows)
+ *   slq_conv_set_packed_weights     attaches it to the handle (all four pointers are DEVICE pointers; NULL wgp
+ *                                   detaches); launches of non-resident / two-limb layers ignore it            */
+SLQ_API int slq_conv_tiling(const slq_conv_desc *d, int32_t *bn_cols, int32_t *n_tiles, int32_t *k_block,
+                            int32_t *num_kb, int32_t *resident);
+SLQ_API int slq_build_packed_gemm_weights(const slq_conv_desc *d, const uint8_t *codes, const int64_t *code_offsets,
+                                          const int32_t *bit, const int64_t *tile_base, const int32_t *seg_bytes,
+                                          const uint16_t *row_offsets, uint8_t *wgp, void *stream);
+SLQ_API int slq_conv_set_packed_weights(slq_conv *c, const uint8_t *wgp, const int64_t *tile_base,
+                                        const int32_t *seg_bytes, const uint16_t *row_offsets);
 SLQ_API void slq_conv_destroy(slq_conv *c);
 
 typedef struct slq_epilogue {

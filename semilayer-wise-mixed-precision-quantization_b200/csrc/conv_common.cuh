@@ -66,6 +66,11 @@ struct slq_conv {
   slq::ConvGeom g_wide;  // 256-channel tiling (valid when wide_ok)
   int wide_ok;           // the layer streams its weights and Cout % 256 == 0: launches without residual use g_wide
   CUtensorMap tmB_wide;
+  // packed weights (slq_conv_set_packed_weights): device pointers, used when the layer keeps its weights resident
+  const uint8_t *wgp;
+  const long long *wgp_tile;
+  const int *wgp_seg;
+  const uint16_t *wgp_rowoff;
   const uint8_t *in;
   const uint8_t *wg;
   int a_im2col;     // 1: A operand through im2col-mode TMA, 0: tiled TMA over [M, Cin]

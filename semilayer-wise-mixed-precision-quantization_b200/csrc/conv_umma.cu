@@ -148,6 +148,12 @@ struct KernelArgs {
   int mma_warps_per_tile;  // MMA warps that touch one tile: 2, or 1 when a tile is a single K block / tile_alt
   int tile_alt;            // the two MMA warps alternate whole tiles instead of pipeline steps
   int acc_bufs, acc_stride;  // TMEM accumulator ring: 3 x 160 columns (N <= 128), 2 x 256 (N = 256)
+  // packed weights (resident-B layers): the n-tile's codes arrive as the PACKED store (4-bit rows two codes per
+  // byte) and are expanded to the u8 operand tiles in shared memory (SURVEY.md H5 / north_star "unpacked in SMEM")
+  const uint8_t *wgp;          // NULL: weights come as u8 through tmB
+  const long long *wgp_tile;   // [n_tiles] byte offset of the n-tile's first (kb = 0) segment
+  const int *wgp_seg;          // [n_tiles] bytes of one (n-tile, kb) segment
+  const uint16_t *wgp_rowoff;  // [n_tiles][bn_cols + 1] byte offset of every row inside a segment
   long long m_tiles;
   long long *trace;    // debug: CTA 0 logs (event, index, clock) triples here (slq_debug_set_trace)
   int trace_cap;
@@ -224,6 +230,7 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c, int bn_ch) {
 
 // OUT: SLQ_OUT_*;  RES: residual kind
 constexpr int kResNone = 0, kResU8 = 1, kResS8 = 2, kResDyn = 3;  // Dyn: decided at run time (fp32/raw outputs)
+constexpr int kResWide = 4;  // no residual, 256-channel tile: quantised outputs are stored straight from registers
 
 template <int SWZ, bool W16, int OUT, int RES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -248,6 +255,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto rempty_bar = [&](int b) { return bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + kMaxResBufs + b); };
   const uint32_t bfull_bar = bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs);  // resident B landed
   auto stfree_bar = [&](int t) { return bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs + 2 + t); };
+  const uint32_t bready_bar = bar_base + 8u * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs + 4);  // packed B expanded
   volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(
       smem + sp.bar_off + 8 * (2 * kMaxStages + 3 * kTileBars + 2 * kMaxResBufs + 1));
 
@@ -259,7 +267,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const EpiDev &e = a.e;
   const int bn_cols = g.bn_cols;
   const int umma_n = bn_cols;
-  const bool has_res = RES == kResDyn ? (e.res != nullptr) : (RES != kResNone);
+  constexpr bool kWide = RES == kResWide;
+  const bool has_res = RES == kResDyn ? (e.res != nullptr) : (RES != kResNone && RES != kResWide);
   const TileWalk walk(a);
 
   // ---- one-time setup -----------------------------------------------------------------------
@@ -268,7 +277,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
-    if (a.tma_out) prefetch_tmap(&tmO);
+    if (!kWide && a.tma_out) prefetch_tmap(&tmO);
     if (has_res) prefetch_tmap(&tmR);
   }
   if (warp == 1 && lane == 0) {
@@ -286,6 +295,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(rempty_bar(b), kTeam);
     }
     mbar_init(bfull_bar, 1);
+    mbar_init(bready_bar, 2 * kTeam);
     mbar_init(stfree_bar(0), 1);
     mbar_init(stfree_bar(1), 1);
     fence_barrier_init();
@@ -324,9 +334,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tx_bytes = (uint32_t)(grp * sp.a_bytes) + (sp.b_resident ? 0u : b_bytes);
     if (warp == 0 && sp.b_resident && walk.count > 0) {  // this CTA's n-tile never changes
       if (elect_one()) {
-        mbar_expect_tx(bfull_bar, b_bytes * (uint32_t)a.num_kb);
-        for (int kb = 0; kb < a.num_kb; ++kb)
-          tma_load_2d(smem_base + sp.b_off + kb * sp.b_tile_bytes, &tmB, bfull_bar, kb * SWZ, walk.my_n * bn_cols);
+        if (a.wgp != nullptr) {
+          // packed store: one bulk copy per K block, landing at the END of the block's operand tile; the
+          // epilogue warps expand it in place (below) before the first MMA
+          const uint32_t seg = (uint32_t)a.wgp_seg[walk.my_n];
+          const uint8_t *src = a.wgp + a.wgp_tile[walk.my_n];
+          mbar_expect_tx(bfull_bar, seg * (uint32_t)a.num_kb);
+          for (int kb = 0; kb < a.num_kb; ++kb)
+            bulk_g2s(smem_base + sp.b_off + (kb + 1) * sp.b_tile_bytes - seg, src + (long long)kb * seg, seg, bfull_bar);
+        } else {
+          mbar_expect_tx(bfull_bar, b_bytes * (uint32_t)a.num_kb);
+          for (int kb = 0; kb < a.num_kb; ++kb)
+            tma_load_2d(smem_base + sp.b_off + kb * sp.b_tile_bytes, &tmB, bfull_bar, kb * SWZ, walk.my_n * bn_cols);
+        }
       }
       __syncwarp();
     }
@@ -459,7 +479,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int items = walk.count * ngrp;
     int tn = 0;
     if (resident && walk.count > 0) {
-      mbar_wait(bfull_bar, 0);  // the CTA's weights are in shared memory
+      mbar_wait(a.wgp != nullptr ? bready_bar : bfull_bar, 0);  // the CTA's weights are in shared memory (as u8)
       tc_fence_after();
     }
     // Which steps this warp issues.  Default: alternate steps (c = w, w + 2, ...), both warps feed the same
@@ -543,6 +563,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (has_res) s_res = kQuant ? __fmul_rn(e.act_scales[e.res_id], inv_out) : e.act_scales[e.res_id];
     }
     const bool res_signed = RES == kResDyn ? (e.res_signed != 0) : (RES == kResS8);
+    // this thread's row inside a staging / residual tile (rows of bn_ch bytes, TMA swizzle of that width)
+    const uint32_t row_byte = (uint32_t)(row * g.bn_ch);
+    const uint32_t row_sw = g.bn_ch == 128 ? (uint32_t)(row & 7) : (uint32_t)((row >> 1) & 3);
     const int units = g.bn_ch / CW;
     const int u0 = half * (units >> 1), u1 = u0 + (units >> 1);
     int last_n_tile = -1;
@@ -586,6 +609,64 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       return sum;
     };
+    if (a.wgp != nullptr && sp.b_resident && walk.count > 0) {
+      // ---- packed weights -> u8 operand tiles, in shared memory (all 16 epilogue warps, once per CTA) ----
+      // Row r of a K block arrives as SWZ/2 bytes (<= 4 bit: two codes per byte, low nibble first) or SWZ bytes
+      // (8 / 6 bit) at offset rowoff[r] of the block's segment, which sits at the END of the block's tile.  A
+      // thread owns (row, 16-byte output chunk) pairs: every source of a tile is read into registers, the
+      // warps meet at a barrier, then every chunk is written to its swizzled place -- reads and writes of the
+      // same tile never overlap in time, so the expansion is in place.
+      const int tid = threadIdx.x - 128;  // 0 .. 511
+      constexpr int kChunks = SWZ / 16;
+      const int n_chunks = bn_cols * kChunks;  // per K block: <= 2048
+      const uint32_t seg = (uint32_t)a.wgp_seg[walk.my_n];
+      const uint16_t *rowoff = a.wgp_rowoff + (long long)walk.my_n * (bn_cols + 1);
+      // this thread's (row, chunk) items: idx = tid + 512 * j
+      uint32_t src_off[4], src_len[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = tid + 512 * j;
+        src_off[j] = 0; src_len[j] = 0;
+        if (idx < n_chunks) {
+          const int r = idx / kChunks, c = idx % kChunks;
+          const uint32_t o0 = rowoff[r], o1 = rowoff[r + 1];
+          const bool half = (o1 - o0) == (uint32_t)(SWZ / 2);  // a 4-bit row
+          src_len[j] = half ? 8u : 16u;
+          src_off[j] = o0 + (uint32_t)c * src_len[j];
+        }
+      }
+      mbar_wait(bfull_bar, 0);
+      for (int kb = 0; kb < a.num_kb; ++kb) {
+        const uint32_t tile_s = smem_base + sp.b_off + kb * sp.b_tile_bytes;
+        const uint32_t raw_s = tile_s + sp.b_tile_bytes - seg;
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (src_len[j] == 16u) v[j] = lds128(raw_s + src_off[j]);
+          else if (src_len[j] == 8u) {
+            uint2 w;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "r"(raw_s + src_off[j]));
+            // 16 nibbles -> 16 bytes: byte 2i = low nibble of byte i, byte 2i+1 = its high nibble
+            const uint32_t l0 = w.x & 0x0f0f0f0fu, h0 = (w.x >> 4) & 0x0f0f0f0fu;
+            const uint32_t l1 = w.y & 0x0f0f0f0fu, h1 = (w.y >> 4) & 0x0f0f0f0fu;
+            v[j] = make_uint4(__byte_perm(l0, h0, 0x5140), __byte_perm(l0, h0, 0x7362), __byte_perm(l1, h1, 0x5140),
+                              __byte_perm(l1, h1, 0x7362));
+          }
+        }
+        named_bar_sync(3, 2 * kTeam);  // every source of this tile is in registers
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int idx = tid + 512 * j;
+          if (src_len[j] != 0u) {
+            const int r = idx / kChunks, c = idx % kChunks;
+            const uint32_t sw = SWZ == 128 ? (uint32_t)(c ^ (r & 7)) : (uint32_t)(c ^ ((r >> 1) & 3));
+            sts128(tile_s + (uint32_t)r * SWZ + (sw << 4), v[j]);
+          }
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(bready_bar);
+    }
     uint32_t S_next = 0;
     if (team < walk.count) {
       int mt0, nt0;
@@ -598,7 +679,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int acc = it % a.acc_bufs, tb = it % kTileBars;
       const uint32_t ph = (uint32_t)((it / kTileBars) & 1);
       // staging tile free again? (the previous TMA store of this team has read it)
-      if (a.tma_out && et == 0) tma_store_wait_read();
+      if (!kWide && a.tma_out && et == 0) tma_store_wait_read();
       named_bar_sync(1 + team, kTeam);
       if (n_tile != last_n_tile && OUT != SLQ_OUT_ACC) {
         if (et < g.bn_ch) {
@@ -638,7 +719,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (has_res) {
 #pragma unroll
           for (int i = 0; i < CW / 16; ++i) {
-            const uint4 r = lds128(rsb + stage_off(row, u * (CW / 16) + i, g.bn_ch));
+            const uint4 r = lds128(rsb + row_byte + ((((uint32_t)(u * (CW / 16) + i)) ^ row_sw) << 4));
             rw[4 * i] = r.x; rw[4 * i + 1] = r.y; rw[4 * i + 2] = r.z; rw[4 * i + 3] = r.w;
           }
         }
@@ -696,12 +777,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (kQuant) {
-          if (a.tma_out) {
+          if constexpr (!kWide) {
             // shared staging tile: the other team's store of the previous tile must have read it
             if (shared_stg && u == u0 && it >= 1) mbar_wait(stfree_bar(team ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
 #pragma unroll
             for (int i = 0; i < CW / 16; ++i)
-              sts128(stg + stage_off(row, u * (CW / 16) + i, g.bn_ch),
+              sts128(stg + row_byte + ((((uint32_t)(u * (CW / 16) + i)) ^ row_sw) << 4),
                      make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]));
           } else if (store_ok) {
             // 256-channel tiles: no staging tile (the smem goes to the {A, B} ring); a thread owns 128 contiguous
@@ -716,7 +797,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
       mbar_arrive(tempty_bar(tb));  // kTeam arrivals release the accumulator buffer
       if (has_res) mbar_arrive(rempty_bar(rbuf));
-      if (a.tma_out) {
+      if (!kWide && a.tma_out) {
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + team, kTeam);
         if (et == 0) {
@@ -733,7 +814,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // round trip to L2 waited for there, once per tile
       if (OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr && valid) atomicAdd(e.out_rowsum + m, rsum);
     }
-    if (a.tma_out && et == 0) tma_store_wait_all();
+    if (!kWide && a.tma_out && et == 0) tma_store_wait_all();
     if (kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && et == 0) { a.trace[6 + team] = wepi; a.trace[12 + team] = clock64() - tstart_clk; }
   }
 
@@ -890,6 +971,9 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   a.sp = make_plan(geom, SWZ, e.res != nullptr);
   a.acc_bufs = wide ? 2 : 3;
   a.acc_stride = wide ? 256 : 160;
+  const bool packed = c->wgp != nullptr && a.sp.b_resident && !W16 && !wide;
+  a.wgp = packed ? c->wgp : nullptr;
+  a.wgp_tile = c->wgp_tile; a.wgp_seg = c->wgp_seg; a.wgp_rowoff = c->wgp_rowoff;
   if (wide) tma_out = 0;  // straight from registers (no staging tile: the smem goes to the operand ring)
   const int grid = plan_grid(geom, a.sp, sm_count());
   a.trace = g_trace;
@@ -925,6 +1009,12 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
 template <int SWZ, bool W16>
 static int launch_umma(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st) {
   const int res = e.res == nullptr ? kResNone : (e.res_signed ? kResS8 : kResU8);
+  if constexpr (SWZ == 128 && !W16) {
+    if (c->wide_ok && res == kResNone) {  // K-heavy layer: 256-channel tiles, quantised outputs straight from registers
+      if (e.out_mode == SLQ_OUT_U8) return launch_one<SWZ, W16, SLQ_OUT_U8, kResWide>(c, e, 0, st);
+      if (e.out_mode == SLQ_OUT_S8) return launch_one<SWZ, W16, SLQ_OUT_S8, kResWide>(c, e, 0, st);
+    }
+  }
   switch (e.out_mode) {
     case SLQ_OUT_U8:
       if (res == kResNone) return launch_one<SWZ, W16, SLQ_OUT_U8, kResNone>(c, e, tma_out, st);
@@ -973,6 +1063,7 @@ extern "C" int slq_conv_create(const slq_conv_desc *d, const uint8_t *in, const 
 #endif
   c->out_ptr = nullptr;
   c->res_ptr = nullptr;
+  c->wgp = nullptr; c->wgp_tile = nullptr; c->wgp_seg = nullptr; c->wgp_rowoff = nullptr;
   const bool can_tile = d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0;
   if (d->a_mode == SLQ_A_TILED && !can_tile) {
     delete c;
@@ -1049,4 +1140,31 @@ extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream
   if (c->swizzle == 128)
     return c->g.w16 ? launch_umma<128, true>(c, e, tma_out, st) : launch_umma<128, false>(c, e, tma_out, st);
   return c->g.w16 ? launch_umma<64, true>(c, e, tma_out, st) : launch_umma<64, false>(c, e, tma_out, st);
+}
+
+extern "C" int slq_conv_tiling(const slq_conv_desc *d, int32_t *bn_cols, int32_t *n_tiles, int32_t *k_block,
+                               int32_t *num_kb, int32_t *resident) {
+  int rc = validate_desc(d);
+  if (rc != SLQ_OK) return rc;
+  const ConvGeom g = make_geom(*d);
+  const int swz = (d->Cin % 128 == 0) ? 128 : 64;
+  if (bn_cols) *bn_cols = g.bn_cols;
+  if (n_tiles) *n_tiles = g.n_tiles;
+  if (k_block) *k_block = swz;
+  if (num_kb) *num_kb = g.Ktot / swz;
+  // resident with AND without a residual tile ring (the caller does not know the epilogue yet)
+  if (resident) *resident = (make_plan(g, swz, true).b_resident && make_plan(g, swz, false).b_resident && !g.w16) ? 1 : 0;
+  return SLQ_OK;
+}
+
+extern "C" int slq_conv_set_packed_weights(slq_conv *c, const uint8_t *wgp, const int64_t *tile_base,
+                                           const int32_t *seg_bytes, const uint16_t *row_offsets) {
+  SLQ_CHECK_ARG(c != nullptr, "slq_conv_set_packed_weights: null handle");
+  SLQ_CHECK_ARG(wgp == nullptr || (tile_base && seg_bytes && row_offsets), "slq_conv_set_packed_weights: layout tables missing");
+  SLQ_CHECK_ARG(reinterpret_cast<uintptr_t>(wgp) % 16 == 0, "slq_conv_set_packed_weights: wgp must be 16-byte aligned");
+  c->wgp = wgp;
+  c->wgp_tile = reinterpret_cast<const long long *>(tile_base);
+  c->wgp_seg = seg_bytes;
+  c->wgp_rowoff = row_offsets;
+  return SLQ_OK;
 }

@@ -66,6 +66,39 @@ __global__ void build_gemm_weights_kernel(ConvGeom g, const uint8_t *__restrict_
   }
 }
 
+// GEMM-ready weights in PACKED form (slq_build_packed_gemm_weights): per n-tile and K block (k_block codes of
+// K in (r, s, c) order) the rows' codes back to back -- rows of <= 4 bits two codes per byte (low nibble first),
+// wider rows one per byte.  One thread per byte of the result.
+__global__ void build_packed_gemm_weights_kernel(ConvGeom g, int swz, const uint8_t *__restrict__ codes,
+                                                 const int64_t *__restrict__ code_offsets,
+                                                 const int32_t *__restrict__ bit, const int64_t *__restrict__ tile_base,
+                                                 const int32_t *__restrict__ seg_bytes,
+                                                 const uint16_t *__restrict__ row_offsets, uint8_t *__restrict__ wgp) {
+  const int num_kb = g.Ktot / swz;
+  const int row = blockIdx.x;  // GEMM row == output channel (one-limb layers only)
+  const int t = row / g.bn_cols, rl = row - t * g.bn_cols;
+  const uint16_t *ro = row_offsets + (long long)t * (g.bn_cols + 1);
+  const int o0 = ro[rl], len = ro[rl + 1] - o0;  // bytes of this row per K block: swz/2 or swz
+  const bool half = len == swz / 2;
+  const int b = row < g.Cout ? bit[row] : 4;
+  const uint8_t *src = row < g.Cout ? codes + code_offsets[row] : nullptr;
+  const int taps = g.kh * g.kw;
+  for (int i = threadIdx.x; i < num_kb * len; i += blockDim.x) {
+    const int kb = i / len, j = i - kb * len;
+    int v = 0;
+    if (src) {
+      const int per = half ? 2 : 1;
+      for (int e = 0; e < per; ++e) {
+        const int k = kb * swz + j * per + e;             // GEMM K index, (r, s, c) order
+        const int tap = k / g.Cin, c = k - tap * g.Cin;
+        const int code = unpack_code(src, (int64_t)c * taps + tap, g.Ktot, b);  // OIHW element (c, r, s)
+        v |= (code & (half ? 15 : 255)) << (4 * e);
+      }
+    }
+    wgp[tile_base[t] + (long long)kb * seg_bytes[t] + o0 + j] = (uint8_t)v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // SIMT convolution (cross-check): thread = (output pixel, output channel)
 // ------------------------------------------------------------------------------------------
@@ -359,5 +392,21 @@ extern "C" int slq_zero_async(void *p, int64_t bytes, void *stream) {
   SLQ_CHECK_ARG(p != nullptr && bytes >= 0, "slq_zero_async: bad argument");
   if (bytes == 0) return SLQ_OK;
   SLQ_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
+  return SLQ_OK;
+}
+
+extern "C" int slq_build_packed_gemm_weights(const slq_conv_desc *d, const uint8_t *codes, const int64_t *code_offsets,
+                                             const int32_t *bit, const int64_t *tile_base, const int32_t *seg_bytes,
+                                             const uint16_t *row_offsets, uint8_t *wgp, void *stream) {
+  int rc = validate_desc(d);
+  if (rc != SLQ_OK) return rc;
+  SLQ_CHECK_ARG(codes && code_offsets && bit && tile_base && seg_bytes && row_offsets && wgp,
+                "slq_build_packed_gemm_weights: null pointer argument");
+  SLQ_CHECK_ARG(!d->w16, "slq_build_packed_gemm_weights: two-limb (never-quantised) layers are not packed");
+  const ConvGeom g = make_geom(*d);
+  const int swz = (d->Cin % 128 == 0) ? 128 : 64;
+  build_packed_gemm_weights_kernel<<<g.gemm_rows, 128, 0, (cudaStream_t)stream>>>(g, swz, codes, code_offsets, bit, tile_base,
+                                                                                 seg_bytes, row_offsets, wgp);
+  SLQ_LAUNCH_CHECK();
   return SLQ_OK;
 }

@@ -452,8 +452,8 @@ constexpr int kTsConvOff = kTsBOff + kSfBBytes;
 constexpr int kTsPrmOff = kTsConvOff + kSfConvRing * kSfConvRowBytes;
 constexpr int kTsBarOff = kTsPrmOff + 64 * 8;
 constexpr int kTsSmemBytes = 1024 + kTsBarOff + 512;
-constexpr int kTsBuildW = 8, kTsMmaW = 4, kTsEpiW = 8;
-constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW;  // producer + builders + MMA + epilogue = 21
+constexpr int kTsBuildW = 8, kTsMmaW = 4, kTsEpiW = 8, kTsPoolW = 4;
+constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW + kTsPoolW;  // producer + builders + MMA + epilogue + pool = 25
 constexpr int kTsThreads = kTsWarps * 32;
 constexpr int kTsBuilders = kTsBuildW * 32, kTsEpi = kTsEpiW * 32;
 constexpr int kTsAccCols = 64, kTsSlabBase = 256, kTsSlotCols = 24;
@@ -503,8 +503,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
   auto pfull_bar = [&](int s) { return bar_base + 8u * (16 + s); };   // pair slabs written to TMEM (8 warps)
   auto pfree_bar = [&](int s) { return bar_base + 8u * (24 + s); };   // the 4 conv rows using the pair are done (4 commits)
   auto tfull_bar = [&](int b) { return bar_base + 8u * (32 + b); };   // accumulator ready (commit)
-  auto tempty_bar = [&](int b) { return bar_base + 8u * (36 + b); };  // accumulator drained (256 threads)
-  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kTsBarOff + 8 * 40);
+  auto tempty_bar = [&](int b) { return bar_base + 8u * (36 + b); };  // accumulator drained (8 epilogue warps)
+  auto vfull_bar = [&](int b) { return bar_base + 8u * (40 + b); };   // vertically pooled row written (8 epilogue warps)
+  auto vfree_bar = [&](int b) { return bar_base + 8u * (44 + b); };   // ... and consumed by the pool warps (4 warps)
+  volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(smem + kTsBarOff + 8 * 48);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   constexpr int ESZ = IN == SLQ_IN_F32 ? 4 : (IN == SLQ_IN_F16 ? 2 : 1);
   const int row_bytes = a.W * ESZ;
@@ -519,7 +521,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     }
     for (int b = 0; b < 4; ++b) {
       mbar_init(tfull_bar(b), 1);
-      mbar_init(tempty_bar(b), kTsEpi);
+      mbar_init(tempty_bar(b), kTsEpiW);
+      mbar_init(vfull_bar(b), kTsEpiW);
+      mbar_init(vfree_bar(b), kTsPoolW);
     }
     fence_barrier_init();
   }
@@ -682,8 +686,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         __syncwarp();
       }
     }
-  } else {
-    // ================================ epilogue + pooling ======================================
+  } else if (warp <= kTsBuildW + kTsMmaW + kTsEpiW) {
+    // ================================ epilogue: accumulator -> u8, vertical half of the pooling ====
     const int et = threadIdx.x - (1 + kTsBuildW + kTsMmaW) * 32;  // 0..255
     const int wq = warp & 3, half = (warp - (1 + kTsBuildW + kTsMmaW)) >> 2;  // TMEM lane quarter, channel half
     const int q = wq * 32 + lane;
@@ -691,7 +695,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     uint8_t *cring = smem + kTsConvOff;
     const bool f32_out = a.out_mode == SLQ_OUT_F32;
     uint32_t vm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // running vertical maximum of the pooling window (packed u8)
-    int rc = 0;
+    int rc = 0, ve = 0;                          // conv rows / pooled rows handled so far by this CTA
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
@@ -703,7 +707,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kTsAccCols + half * 32, av);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(tempty_bar(acc));  // accumulator is in registers: row rc + 4 may start
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: row rc + 4 may start
         if (SF_DBG(a) & 4) continue;
         float y[32];
 #pragma unroll
@@ -743,38 +748,61 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         // of a unit belongs to the previous unit's pooled row and only opens this unit's first window
         const bool emit = ((p & 1) || p == a.Hc - 1) && jrow >= j0 && p != p0;
         if (emit) {
-          uint4 *dst = reinterpret_cast<uint4 *>(cring + (jrow & 1) * kSfConvRowBytes + q * 64 + half * 32);
+          // hand the vertically pooled row to the pool warps through a 4-slot ring
+          const int vs = ve & 3;
+          if (ve >= 4) mbar_wait(vfree_bar(vs), (uint32_t)(((ve >> 2) & 1) ^ 1));
+          uint4 *dst = reinterpret_cast<uint4 *>(cring + vs * kSfConvRowBytes + q * 64 + half * 32);
           dst[0] = make_uint4(vm[0], vm[1], vm[2], vm[3]);
           dst[1] = make_uint4(vm[4], vm[5], vm[6], vm[7]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(vfull_bar(vs));
+          ++ve;
         }
         if (p & 1) {  // an odd row also opens the next window
 #pragma unroll
           for (int j = 0; j < 8; ++j) vm[j] = pk[j];
         }
-        if (!emit) continue;
-        named_bar_sync(2, kTsEpi);  // the vertically pooled row is complete in its slot (2 slots alternate)
-        const uint8_t *vrow = cring + (jrow & 1) * kSfConvRowBytes;
-        uint4 *orow = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) +
-                                                (((long long)n * a.Hp + jrow) * a.Wp) * 64);
-        uint32_t *rsrow = a.out_rowsum ? a.out_rowsum + ((long long)n * a.Hp + jrow) * a.Wp : nullptr;
-        for (int base = et & ~31; base < a.Wp * 4; base += kTsEpi) {  // whole warps walk the loop (shuffles below)
-          const int idx = base + lane;
-          const bool live = idx < a.Wp * 4;
-          const int i = idx >> 2, gch = (idx & 3) * 16;
-          uint4 m = make_uint4(0, 0, 0, 0);
-          if (live) {
-            // clamped columns: a duplicated column does not change a maximum
-            const int c0 = max(2 * i - 1, 0) * 64 + gch, c1 = 2 * i * 64 + gch, c2 = min(2 * i + 1, a.Wc - 1) * 64 + gch;
-            m = *reinterpret_cast<const uint4 *>(vrow + c0);
-            const uint4 v1 = *reinterpret_cast<const uint4 *>(vrow + c1), v2 = *reinterpret_cast<const uint4 *>(vrow + c2);
-            m.x = __vmaxu4(__vmaxu4(m.x, v1.x), v2.x); m.y = __vmaxu4(__vmaxu4(m.y, v1.y), v2.y);
-            m.z = __vmaxu4(__vmaxu4(m.z, v1.z), v2.z); m.w = __vmaxu4(__vmaxu4(m.w, v1.w), v2.w);
-            orow[idx] = m;
+      }
+    }
+  } else {
+    // ================================ pool warps: horizontal half of the pooling, stores ============
+    // (their own role, so that the epilogue warps' chain per conv row -- wait, tcgen05.ld, convert -- never waits
+    // for a pooled row to be written out)
+    const int pt = threadIdx.x - (1 + kTsBuildW + kTsMmaW + kTsEpiW) * 32;  // 0..127
+    const uint8_t *cring = smem + kTsConvOff;
+    int ve = 0;
+    if (a.out_mode != SLQ_OUT_F32) {
+      for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
+        int n, j0, j1, p0, p1;
+        unit_rows(a, u, n, j0, j1, p0, p1);
+        for (int jrow = j0; jrow < j1; ++jrow, ++ve) {
+          const int vs = ve & 3;
+          mbar_wait(vfull_bar(vs), (uint32_t)((ve >> 2) & 1));
+          const uint8_t *vrow = cring + vs * kSfConvRowBytes;
+          uint4 *orow = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) +
+                                                  (((long long)n * a.Hp + jrow) * a.Wp) * 64);
+          uint32_t *rsrow = a.out_rowsum ? a.out_rowsum + ((long long)n * a.Hp + jrow) * a.Wp : nullptr;
+          for (int base = pt & ~31; base < a.Wp * 4 && !(SF_DBG(a) & 16); base += kTsPoolW * 32) {  // whole warps (shuffles below)
+            const int idx = base + lane;
+            const bool live = idx < a.Wp * 4;
+            const int i = idx >> 2, gch = (idx & 3) * 16;
+            uint4 m = make_uint4(0, 0, 0, 0);
+            if (live) {
+              // clamped columns: a duplicated column does not change a maximum
+              const int c0 = max(2 * i - 1, 0) * 64 + gch, c1 = 2 * i * 64 + gch, c2 = min(2 * i + 1, a.Wc - 1) * 64 + gch;
+              m = *reinterpret_cast<const uint4 *>(vrow + c0);
+              const uint4 v1 = *reinterpret_cast<const uint4 *>(vrow + c1), v2 = *reinterpret_cast<const uint4 *>(vrow + c2);
+              m.x = __vmaxu4(__vmaxu4(m.x, v1.x), v2.x); m.y = __vmaxu4(__vmaxu4(m.y, v1.y), v2.y);
+              m.z = __vmaxu4(__vmaxu4(m.z, v1.z), v2.z); m.w = __vmaxu4(__vmaxu4(m.w, v1.w), v2.w);
+              orow[idx] = m;
+            }
+            uint32_t ps = __dp4a(m.x, 0x01010101u, __dp4a(m.y, 0x01010101u, __dp4a(m.z, 0x01010101u, __dp4a(m.w, 0x01010101u, 0u))));
+            ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+            ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+            if (live && rsrow && (idx & 3) == 0) rsrow[i] = ps;
           }
-          uint32_t ps = __dp4a(m.x, 0x01010101u, __dp4a(m.y, 0x01010101u, __dp4a(m.z, 0x01010101u, __dp4a(m.w, 0x01010101u, 0u))));
-          ps += __shfl_xor_sync(0xffffffffu, ps, 1);
-          ps += __shfl_xor_sync(0xffffffffu, ps, 2);
-          if (live && rsrow && (idx & 3) == 0) rsrow[i] = ps;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(vfree_bar(vs));
         }
       }
     }

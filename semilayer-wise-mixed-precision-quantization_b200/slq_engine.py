@@ -75,6 +75,54 @@ def classify_weights(weights, stream=None):
     return out
 
 
+class PackedGemm:
+    """GEMM-ready weights of one conv in PACKED form (include/slq.h, slq_conv_set_packed_weights): what the
+    tcgen05 kernel of a resident-weight layer fetches and unpacks in shared memory."""
+
+    def __init__(self, blob, tile_base, seg_bytes, row_offsets):
+        self.blob, self.tile_base, self.seg_bytes, self.row_offsets = blob, tile_base, seg_bytes, row_offsets
+
+    @property
+    def nbytes(self):
+        return int(self.blob.numel())
+
+
+def conv_tiling(desc):
+    lib = L.lib()
+    v = [ctypes.c_int32(0) for _ in range(5)]
+    L.check(lib.slq_conv_tiling(ctypes.byref(desc), *[ctypes.addressof(x) for x in v]))
+    return tuple(int(x.value) for x in v)  # bn_cols, n_tiles, k_block, num_kb, resident
+
+
+def build_packed_gemm(desc, packed, bits_host, device, stream=None):
+    """Layout tables (numpy, from the per-channel bit-widths) + slq_build_packed_gemm_weights.  Returns None
+    when the kernel does not keep this layer's weights resident (they are then streamed as u8 tiles)."""
+    lib = L.lib()
+    bn_cols, n_tiles, k_block, num_kb, resident = conv_tiling(desc)
+    if not resident or int(bits_host.max()) > 8:
+        return None
+    stream = L.current_stream() if stream is None else stream
+    rows = bn_cols * n_tiles
+    bits = np.full(rows, 4, np.int64)
+    bits[:len(bits_host)] = bits_host
+    seg = np.where(bits <= 4, k_block // 2, k_block).reshape(n_tiles, bn_cols)
+    row_off = np.zeros((n_tiles, bn_cols + 1), np.int64)
+    row_off[:, 1:] = np.cumsum(seg, axis=1)
+    seg_bytes = row_off[:, -1].astype(np.int32)
+    tile_base = np.zeros(n_tiles, np.int64)
+    tile_base[1:] = np.cumsum(num_kb * seg_bytes.astype(np.int64))[:-1]
+    total = int(num_kb * seg_bytes.astype(np.int64).sum())
+    assert row_off.max() < 65536
+    blob = torch.empty(max(total, 16), dtype=torch.uint8, device=device)
+    tb = torch.from_numpy(tile_base).to(device)
+    sb = torch.from_numpy(seg_bytes).to(device)
+    ro = torch.from_numpy(row_off.astype(np.uint16).view(np.int16)).to(device)
+    L.check(lib.slq_build_packed_gemm_weights(ctypes.byref(desc), packed.blob.data_ptr(), packed.offsets.data_ptr(),
+                                              packed.bits.data_ptr(), tb.data_ptr(), sb.data_ptr(), ro.data_ptr(),
+                                              blob.data_ptr(), stream))
+    return PackedGemm(blob, tb, sb, ro)
+
+
 def encode_weight(w, bit, z, s, bits_host, stream=None):
     lib = L.lib()
     stream = L.current_stream() if stream is None else stream
@@ -92,12 +140,13 @@ class _ConvOp:
 
 
 class Engine:
-    def __init__(self, net, N, H, W, device, impl=L.IMPL_UMMA, a_mode=L.A_AUTO, stem="umma"):
+    def __init__(self, net, N, H, W, device, impl=L.IMPL_UMMA, a_mode=L.A_AUTO, stem="umma", packed_b=True):
         if device.type != "cuda":
             raise RuntimeError("slq Engine needs a CUDA device")
         self.lib = L.lib()
         self.net, self.N, self.H, self.W, self.device = net, N, H, W, device
         self.impl, self.a_mode = impl, a_mode
+        self.packed_b = packed_b  # resident-weight layers fetch PACKED codes and unpack them in shared memory
         self.stem_kind = stem  # "umma": tcgen05 fp16 stem; "simt": exact-fp32 CUDA-core stem
         self.stem = None
         self.epoch = -1
@@ -216,6 +265,7 @@ class Engine:
         op.res_id, op.res_signed = -1, False
         op.handle, op.w16 = None, None
         op.variants = {}          # w16 -> (desc, GEMM-ready weight buffer, conv handle); created once, kept
+        op.packed_gemm = None     # PackedGemm of the current weights (resident-weight layers)
         op.wsig = op.bsig = None  # what was packed last (see _sig)
         dev = self.device
         op.wscale = torch.zeros(op.Cout, dtype=torch.float32, device=dev)
@@ -286,8 +336,14 @@ class Engine:
                     L.check(lib.slq_build_gemm_weights(ctypes.byref(desc), op.packed.blob.data_ptr(),
                                                        op.packed.offsets.data_ptr(), op.packed.bits.data_ptr(),
                                                        wg.data_ptr(), stream))
-                    if op.w16 != w16:  # one-limb <-> two-limb: another kernel variant, graphs are stale
-                        self._graphs, self._seen = {}, set()
+                    # resident-weight layers take their B operand PACKED (4-bit rows two codes per byte), unpacked in
+                    # shared memory; the u8 matrix above stays the operand of the streamed layers and of the SIMT checker
+                    pg = build_packed_gemm(desc, op.packed, bits_host, dev, stream) if (self.packed_b and self.impl == L.IMPL_UMMA) else None
+                    L.check(lib.slq_conv_set_packed_weights(h, L.ptr(pg.blob if pg else None), L.ptr(pg.tile_base if pg else None),
+                                                            L.ptr(pg.seg_bytes if pg else None), L.ptr(pg.row_offsets if pg else None)))
+                    if (op.packed_gemm is None) != (pg is None) or op.w16 != w16:
+                        self._graphs, self._seen = {}, set()  # another kernel variant / other pointers: graphs are stale
+                    op.packed_gemm = pg
                     op.handle, op.w16, op.desc, op.wg = h, w16, desc, wg
                     op.s_dev, op.z_dev = s, z
                     self._fold_into(op)

@@ -53,6 +53,9 @@ SIGNATURES = {
     "slq_build_gemm_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
     "slq_conv_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, ctypes.POINTER(_vp)]),
     "slq_conv_destroy": (None, [_vp]),
+    "slq_conv_tiling": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp]),
+    "slq_build_packed_gemm_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "slq_conv_set_packed_weights": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "slq_conv_launch": (ctypes.c_int, [_vp, ctypes.POINTER(Epilogue), _vp]),
     "slq_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
     "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),

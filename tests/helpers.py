@@ -71,7 +71,7 @@ def codes_ohwi(meta, cout, cin, k):
 class ConvCase:
     """One conv layer on the device, built through the C ABI exactly like slq_engine does."""
 
-    def __init__(self, N, H, cin, cout, k, stride, bits, seed=0, impl=None, a_mode=0, device="cuda"):
+    def __init__(self, N, H, cin, cout, k, stride, bits, seed=0, impl=None, a_mode=0, device="cuda", packed_b=False):
         import slq_engine
         import slq_lib as L
         self.L = L
@@ -99,6 +99,13 @@ class ConvCase:
         h = ctypes.c_void_p()
         L.check(lib.slq_conv_create(ctypes.byref(self.desc), self.xd.data_ptr(), self.wg.data_ptr(), ctypes.byref(h)))
         self.handle = h
+        self.packed_gemm = None
+        if packed_b:  # B operand as the packed store, unpacked in shared memory (resident-weight layers)
+            self.packed_gemm = slq_engine.build_packed_gemm(self.desc, self.packed, self.bits_host, device)
+            if self.packed_gemm is not None:
+                pg = self.packed_gemm
+                L.check(lib.slq_conv_set_packed_weights(h, pg.blob.data_ptr(), pg.tile_base.data_ptr(),
+                                                        pg.seg_bytes.data_ptr(), pg.row_offsets.data_ptr()))
         self.Ho = (H + 2 * self.pad - k) // stride + 1
         self.M = N * self.Ho * self.Ho
         self.device = device

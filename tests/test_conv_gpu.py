@@ -192,3 +192,56 @@ def test_umma_equals_simt_epilogue_modes_multi_tile(cfg):
     assert np.array_equal(oa, ob)
     a.close()
     b.close()
+
+
+def _expected_packed_gemm(case, bn_cols, n_tiles, k_block, num_kb):
+    """numpy restatement of the packed GEMM-ready layout (include/slq.h, slq_conv_set_packed_weights)."""
+    cout, cin, k = case.cout, case.cin, case.k
+    codes = np.zeros((bn_cols * n_tiles, k * k * cin), np.int64)
+    bits = np.full(bn_cols * n_tiles, 4, np.int64)
+    for oc in range(cout):
+        codes[oc] = case.meta[oc][1].reshape(cin, k, k).transpose(1, 2, 0).reshape(-1)  # (c,r,s) -> (r,s,c)
+        bits[oc] = case.meta[oc][0]
+    out = []
+    for t in range(n_tiles):
+        for kb in range(num_kb):
+            for r in range(t * bn_cols, (t + 1) * bn_cols):
+                seg = codes[r, kb * k_block:(kb + 1) * k_block]
+                if bits[r] <= 4:
+                    out.append((seg[0::2] | (seg[1::2] << 4)).astype(np.uint8))
+                else:
+                    out.append(seg.astype(np.uint8))
+    return np.concatenate(out)
+
+
+@pytest.mark.parametrize("shape", [(64, 256, 1, 1, 56), (256, 64, 1, 1, 56), (64, 64, 3, 1, 56), (512, 128, 1, 1, 28),
+                                   (128, 512, 1, 1, 28), (64, 64, 1, 1, 56), (512, 2048, 1, 1, 7)],
+                         ids=lambda s: "c%d-%d_k%d_s%d_h%d" % s)
+def test_umma_packed_weights_unpacked_in_shared_memory(shape):
+    """BASELINE north_star: 4-bit semilayer codes travel PACKED (two per byte) and are unpacked to int8 in shared
+    memory.  Resident-weight layers with scattered 4/8-bit rows: the packed operand is what the layout says, it
+    is smaller than the u8 matrix, and accumulators / epilogues stay bit-exact."""
+    import slq_engine
+    cin, cout, k, stride, H = shape
+    bits = _mixed_bits(cout, cin + 3 * cout)
+    case = ConvCase(2, H, cin, cout, k, stride, bits, seed=cout + 7, packed_b=True)
+    assert case.packed_gemm is not None
+    bn_cols, n_tiles, k_block, num_kb, resident = slq_engine.conv_tiling(case.desc)
+    assert resident == 1
+    want = _expected_packed_gemm(case, bn_cols, n_tiles, k_block, num_kb)
+    got = case.packed_gemm.blob.cpu().numpy()[:want.size]
+    assert np.array_equal(got, want)
+    n4 = int((bits == 4).sum())
+    assert want.size == (k * k * cin) * (cout - n4) + (k * k * cin // 2) * n4  # Cout is a multiple of the tile here
+    assert want.size < case.wg.numel()
+    _check_acc(case)
+    _check_epilogues(case, 23)
+    case.close()
+
+
+def test_streamed_layers_keep_the_u8_operand():
+    import slq_engine
+    case = ConvCase(2, 14, 256, 256, 3, 1, _mixed_bits(256, 9), seed=3, packed_b=True)
+    assert slq_engine.conv_tiling(case.desc)[4] == 0 and case.packed_gemm is None
+    _check_acc(case)
+    case.close()
