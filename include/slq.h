@@ -211,12 +211,15 @@ typedef struct slq_epilogue {
   int32_t out_mode;
   int32_t relu;
   /* Per-pixel channel sums ("rowsum") of u8 activations: the zero-point term z[oc] * S[m] needs the window sum
-   * S[m] of the INPUT; the tcgen05 kernel gathers it from in_rowsum (<= 9 taps) instead of spending tensor
-   * work on a row of ones.  Every producer of a u8 activation fills the side tensor of its output:       */
-  const uint32_t *in_rowsum; /* [N*H*W] sum over Cin of the input pixel (required by SLQ_IMPL_UMMA;
-                                the SIMT checker computes S itself and ignores it)                       */
-  uint32_t *out_rowsum;      /* [M] SLQ_OUT_U8 only, may be NULL: += sum over Cout of the u8 output pixel
-                                (atomic adds from the n-tiles: the caller zeroes it before the launch)   */
+   * S[m] of the INPUT; the tcgen05 kernel gathers it from side tensors instead of spending tensor work on a row
+   * of ones.  A side tensor is a stack of PLANES of one uint32 per pixel; the channel sum of a pixel is the sum
+   * of its planes (every n-tile of the producing launch writes its own plane with plain stores: no atomics,
+   * nothing to zero).                                                                                       */
+  const uint32_t *in_rowsum; /* [in_planes][in_plane_stride], in_plane_stride >= N*H*W pixels of the input
+                                (required by SLQ_IMPL_UMMA; the SIMT checker computes S itself and ignores it) */
+  uint32_t *out_rowsum;      /* SLQ_OUT_U8 only, may be NULL: [slq_conv_rowsum_planes()][M] planes of the output */
+  int32_t in_planes;
+  int64_t in_plane_stride;
 } slq_epilogue;
 
 /* Debug timeline: when buf != NULL, CTA 0 of every later slq_conv_launch logs (event+1, index, SM clock)
@@ -225,9 +228,9 @@ typedef struct slq_epilogue {
  * epilogue tile begin/end.  NULL switches tracing off.  Not for production use.                    */
 SLQ_API int slq_debug_set_trace(int64_t *buf, int32_t capacity_events);
 
-/* cudaMemsetAsync(p, 0, bytes) on `stream`: zeroes the rowsum side tensors at the start of a forward pass
- * (captured as a memset node when the forward is recorded into a CUDA graph).                        */
-SLQ_API int slq_zero_async(void *p, int64_t bytes, void *stream);
+/* Planes a launch of this layer writes into slq_epilogue.out_rowsum (= n-tiles of the tiling it will use, which
+ * depends on whether the launch has a residual); 0 for the SIMT checker.                                  */
+SLQ_API int32_t slq_conv_rowsum_planes(const slq_conv *c, int32_t has_residual);
 
 /* y[m, oc] = (acc[m,oc] + z[oc] * S[m]) * wscale[oc] * act_scales[in_id] + bias[oc]
  *            (+ res[m,oc] * act_scales[res_id]) ; ReLU ; u8 = clamp(rint(y / act_scales[out_id])) */
@@ -240,8 +243,8 @@ SLQ_API int slq_conv_launch(slq_conv *c, const slq_epilogue *e, void *stream);
 /* Stem: resnet.py:206-209  conv1 7x7 s2 p3 (3->64, fp32 weights) + bn1 + relu + maxpool 3x3 s2 p1.
  * x fp32 NCHW [N,3,H,W] -> out NHWC [N,Hp,Wp,64], Hp = ((H+1)/2+1)/2 (u8 via act_scales[out_id], or
  * fp32 when out_mode == SLQ_OUT_F32).  `scratch` holds the pre-pool activations:
- * N*Hc*Wc*64 floats with Hc = (H+1)/2.  out_rowsum (SLQ_OUT_U8, may be NULL): [N*Hp*Wp] += channel sum of
- * every output pixel (see slq_epilogue.in_rowsum; zeroed by the caller).                          */
+ * N*Hc*Wc*64 floats with Hc = (H+1)/2.  out_rowsum (SLQ_OUT_U8, may be NULL): [N*Hp*Wp] channel sum of
+ * every output pixel: the single rowsum plane of the stem's output (see slq_epilogue.in_rowsum).        */
 SLQ_API int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W, const float *w,
                      const float *bn_a, const float *bn_b, const float *act_scales, int32_t out_id,
                      float *scratch, void *out, int32_t out_mode, uint32_t *out_rowsum, void *stream);

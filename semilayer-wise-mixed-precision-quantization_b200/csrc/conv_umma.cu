@@ -8,9 +8,11 @@
 //       (zero padding and the (r,s) filter offsets are resolved by the TMA unit), tiled map for
 //       1x1 stride-1 layers;  B = GEMM-ready weight codes [rows, K], K ordered (r, s, c).
 //   The zero-point correction z[oc]*S[m] needs the window sum S[m] = sum_k A[m, k]: every
-//   producer of a u8 activation also accumulates its per-pixel channel sums into a side tensor
-//   (rowsum, 4 bytes per pixel: one DP4A per four outputs + one RED per thread and tile), and the consumer's
-//   epilogue gathers the <= 9 taps of its window from it.  (Round 1 appended a row of ones to every B tile
+//   producer of a u8 activation also writes its per-pixel channel sums into a side tensor (rowsum: one PLANE
+//   of 4 bytes per pixel per n-tile of the producer -- one DP4A per four outputs, the two half-tile warps
+//   combine through shared memory, one coalesced 4-byte store per pixel and tile; atomics cost ~1.3 cycles per
+//   lane on the SM and were what the epilogue-bound layers then waited for), and the consumer's epilogue adds
+//   the planes over the <= 9 taps of its window, one tile ahead of the accumulator it is needed for.  (Round 1 appended a row of ones to every B tile
 //   instead: N = 144, 12.5 % more tensor work and no room for the N = 256 tiles below.)
 //   K-heavy layers (weights streamed, Cout % 256 == 0) run 256-channel tiles: UMMA N = 256 is the shape at
 //   which one tcgen05.mma occupies the tensor pipe for as long as a warp needs to issue the next one
@@ -70,7 +72,7 @@ struct SmemPlan {
 };
 
 constexpr int kMaxResBufs = 4;
-constexpr int kPrmBytes = 2 * 3 * 256 * 4;  // per team: A[256] | Z[256] | B[256] floats
+constexpr int kPrmBytes = 2 * 3 * 256 * 4 + 2 * 128 * 4;  // per team: A[256] | Z[256] | B[256] floats; then 128 u32 of row-sum scratch per team
 constexpr int kMaxGroup = 4;
 
 inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
@@ -553,6 +555,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // data pipe was the busiest unit of the epilogue with one {A,Z,B,pad} load per output), so one load
     // fetches the same constant of FOUR channels: 3 wavefronts per channel instead of 4, 0.75 loads per output.
     float *prm = reinterpret_cast<float *>(smem + sp.prm_off) + team * 768;
+    volatile uint32_t *rs_scratch = reinterpret_cast<volatile uint32_t *>(smem + sp.prm_off + 2 * 3072) + team * 128;
     const uint32_t prm_s = smem_base + sp.prm_off + team * 3072;
     const bool shared_stg = sp.out_bufs == 1;  // both teams stage through one tile (stfree hand-off below)
     const uint32_t stg = smem_base + sp.out_off + (shared_stg ? 0 : team) * kOutTileBytes;
@@ -579,7 +582,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float inv_hw = __frcp_rn((float)(g.Ho * g.Wo)), inv_wo = __frcp_rn((float)g.Wo);
     auto window_sum = [&](int mm) -> uint32_t {
       if (mm >= g.M) return 0u;
-      if (same_grid) return __ldg(e.in_rowsum + mm);
+      if (same_grid) {
+        uint32_t sum = 0;
+        for (int pl = 0; pl < e.in_planes; ++pl) sum += __ldg(e.in_rowsum + (long long)pl * e.in_plane_stride + mm);
+        return sum;
+      }
       const int hw = g.Ho * g.Wo;
       int n_img, rem, ho, wo;
       if (g.M < (1 << 24)) {  // every index is an exact float: the reciprocal quotient is off by at most one
@@ -593,18 +600,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         n_img = mm / hw; rem = mm - n_img * hw;
         ho = rem / g.Wo; wo = rem - ho * g.Wo;
       }
-      const uint32_t *rs = e.in_rowsum + (long long)n_img * g.H * g.W;
-      if (g.kh == 1) return __ldg(rs + (ho * g.stride) * g.W + wo * g.stride);
-      const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
       uint32_t sum = 0;
+      for (int pl = 0; pl < e.in_planes; ++pl) {
+        const uint32_t *rs = e.in_rowsum + (long long)pl * e.in_plane_stride + (long long)n_img * g.H * g.W;
+        if (g.kh == 1) { sum += __ldg(rs + (ho * g.stride) * g.W + wo * g.stride); continue; }
+        const int h0 = ho * g.stride - g.pad, w0 = wo * g.stride - g.pad;
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int hi = h0 + r;
-        if (hi < 0 || hi >= g.H) continue;
+        for (int r = 0; r < 3; ++r) {
+          const int hi = h0 + r;
+          if (hi < 0 || hi >= g.H) continue;
 #pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          const int wi = w0 + q;
-          if (wi >= 0 && wi < g.W) sum += __ldg(rs + hi * g.W + wi);
+          for (int q = 0; q < 3; ++q) {
+            const int wi = w0 + q;
+            if (wi >= 0 && wi < g.W) sum += __ldg(rs + hi * g.W + wi);
+          }
         }
       }
       return sum;
@@ -793,11 +802,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      const bool want_rs = OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr;
+      if (want_rs && half == 1) rs_scratch[row] = rsum;  // the other half of the tile's channels adds it below
       tc_fence_before();
       if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
       mbar_arrive(tempty_bar(tb));  // kTeam arrivals release the accumulator buffer
       if (has_res) mbar_arrive(rempty_bar(rbuf));
-      if (!kWide && a.tma_out) {
+      if (kWide || !a.tma_out) {
+        if (want_rs) named_bar_sync(1 + team, kTeam);  // the scratch row sums are visible
+      } else {
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + team, kTeam);
         if (et == 0) {
@@ -812,7 +825,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // per-pixel channel sum of this tile's u8 outputs -> side tensor of the output activation.  LAST in the
       // iteration: a fire-and-forget reduction issued before the proxy fence / barrier above would have its
       // round trip to L2 waited for there, once per tile
-      if (OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr && valid) atomicAdd(e.out_rowsum + m, rsum);
+      if (OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr && half == 0 && valid)
+        e.out_rowsum[(long long)n_tile * g.M + m] = rsum + rs_scratch[row];  // plane n_tile: the whole tile's channels
     }
     if (!kWide && a.tma_out && et == 0) tma_store_wait_all();
     if (kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && et == 0) { a.trace[6 + team] = wepi; a.trace[12 + team] = clock64() - tstart_clk; }
@@ -1118,6 +1132,7 @@ extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream
   EpiDev e;
   e.wscale = ep->wscale; e.zf = ep->zf; e.bias = ep->bias; e.act_scales = ep->act_scales;
   e.in_rowsum = ep->in_rowsum; e.out_rowsum = ep->out_rowsum;
+  e.in_planes = ep->in_planes; e.in_plane_stride = ep->in_plane_stride;
   e.res = ep->out_mode == SLQ_OUT_ACC ? nullptr : ep->res;
   e.out = ep->out; e.out_S = ep->out_S;
   e.in_id = ep->in_id; e.out_id = ep->out_id; e.res_id = ep->res_id;
@@ -1125,7 +1140,8 @@ extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream
   e.Cout = c->g.Cout; e.w16 = c->g.w16; e.M = c->g.M;
   cudaStream_t st = (cudaStream_t)stream;
   if (c->desc.impl == SLQ_IMPL_SIMT) return launch_conv_simt(c->g, c->in, c->wg, e, st);
-  SLQ_CHECK_ARG(ep->in_rowsum != nullptr, "slq_conv_launch: in_rowsum (per-pixel channel sums of the input) is NULL");
+  SLQ_CHECK_ARG(ep->in_rowsum != nullptr && ep->in_planes >= 1 && ep->in_plane_stride >= (int64_t)c->g.N * c->g.H * c->g.W,
+                "slq_conv_launch: in_rowsum (per-pixel channel sums of the input: planes, plane stride) missing");
   const int tma_out = (ep->out_mode == SLQ_OUT_U8 || ep->out_mode == SLQ_OUT_S8) ? 1 : 0;
   if (tma_out && c->out_ptr != ep->out) {  // (re)encode the store map for this output buffer
     int rc = encode_out_map(&c->tmO, ep->out, c->g, "out");
@@ -1167,4 +1183,10 @@ extern "C" int slq_conv_set_packed_weights(slq_conv *c, const uint8_t *wgp, cons
   c->wgp_seg = seg_bytes;
   c->wgp_rowoff = row_offsets;
   return SLQ_OK;
+}
+
+extern "C" int32_t slq_conv_rowsum_planes(const slq_conv *c, int32_t has_residual) {
+  if (!c) return -1;
+  if (c->desc.impl != SLQ_IMPL_UMMA) return 0;  // the SIMT checker computes its own window sums and writes none
+  return (c->wide_ok && !has_residual && !c->g.w16) ? c->g_wide.n_tiles : c->g.n_tiles;
 }

@@ -33,8 +33,10 @@ struct EpiDev {  // device-side view of slq_epilogue (+ layer constants)
   const uint8_t *res;
   void *out;
   int32_t *out_S;
-  const uint32_t *in_rowsum;  // [N*H*W] per-pixel channel sums of the INPUT activation (tcgen05 path)
-  uint32_t *out_rowsum;       // [M] per-pixel channel sums of the u8 OUTPUT, accumulated with atomics (or NULL)
+  const uint32_t *in_rowsum;  // [in_planes][in_plane_stride] per-pixel channel sums of the INPUT activation: the sum of the planes
+  uint32_t *out_rowsum;       // [n_tiles][M] per-pixel sums over each n-tile's channels of the u8 OUTPUT (or NULL)
+  int in_planes;
+  long long in_plane_stride;
   int in_id, out_id, res_id;
   int out_mode, relu, res_signed;
   int Cout, w16;

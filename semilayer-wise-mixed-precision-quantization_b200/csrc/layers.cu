@@ -262,7 +262,13 @@ __global__ void __launch_bounds__(256) stem_pool_kernel(const float *__restrict_
     const uint32_t q = epi_quant_u8(__fmul_rn(m.x, inv)) | (epi_quant_u8(__fmul_rn(m.y, inv)) << 8) |
                        (epi_quant_u8(__fmul_rn(m.z, inv)) << 16) | (epi_quant_u8(__fmul_rn(m.w, inv)) << 24);
     *reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(out) + pix * 64 + og * 4) = q;
-    if (out_rowsum) atomicAdd(out_rowsum + pix, __dp4a(q, 0x01010101u, 0u));
+    if (out_rowsum) {  // the 16 threads of a pixel are 16 neighbouring lanes (total is a multiple of 16: no lane is missing)
+      uint32_t ps = __dp4a(q, 0x01010101u, 0u);
+      const unsigned live = __activemask();  // threads past the end left in whole groups of 16
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) ps += __shfl_xor_sync(live, ps, o, 16);
+      if (og == 0) out_rowsum[pix] = ps;
+    }
   }
 }
 
@@ -385,13 +391,6 @@ extern "C" int slq_quantize_act(const float *y, int64_t n, const float *act_scal
   const int blocks = (int)std::min<int64_t>(ceil_div(n / 4 + 1, 256), (int64_t)sm_count() * 8);
   quantize_act_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(y, n, act_scales, id, is_signed, out);
   SLQ_LAUNCH_CHECK();
-  return SLQ_OK;
-}
-
-extern "C" int slq_zero_async(void *p, int64_t bytes, void *stream) {
-  SLQ_CHECK_ARG(p != nullptr && bytes >= 0, "slq_zero_async: bad argument");
-  if (bytes == 0) return SLQ_OK;
-  SLQ_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, (cudaStream_t)stream));
   return SLQ_OK;
 }
 

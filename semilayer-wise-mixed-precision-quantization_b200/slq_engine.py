@@ -81,10 +81,11 @@ class PackedGemm:
 
     def __init__(self, blob, tile_base, seg_bytes, row_offsets):
         self.blob, self.tile_base, self.seg_bytes, self.row_offsets = blob, tile_base, seg_bytes, row_offsets
+        self.used_bytes = 0
 
     @property
     def nbytes(self):
-        return int(self.blob.numel())
+        return self.used_bytes
 
 
 def conv_tiling(desc):
@@ -94,14 +95,29 @@ def conv_tiling(desc):
     return tuple(int(x.value) for x in v)  # bn_cols, n_tiles, k_block, num_kb, resident
 
 
-def build_packed_gemm(desc, packed, bits_host, device, stream=None):
-    """Layout tables (numpy, from the per-channel bit-widths) + slq_build_packed_gemm_weights.  Returns None
-    when the kernel does not keep this layer's weights resident (they are then streamed as u8 tiles)."""
+def alloc_packed_gemm(desc, device):
+    """Persistent buffers for the packed operand of one layer (worst case: every row 8-bit), or None when the
+    kernel does not keep this layer's weights resident.  Their ADDRESSES never change -- a re-pack rewrites the
+    contents in place -- so conv handles and captured CUDA graphs stay valid."""
+    bn_cols, n_tiles, k_block, num_kb, resident = conv_tiling(desc)
+    if not resident:
+        return None
+    blob = torch.zeros(bn_cols * n_tiles * k_block * num_kb, dtype=torch.uint8, device=device)
+    return PackedGemm(blob, torch.zeros(n_tiles, dtype=torch.int64, device=device),
+                      torch.zeros(n_tiles, dtype=torch.int32, device=device),
+                      torch.zeros((n_tiles, bn_cols + 1), dtype=torch.int16, device=device))
+
+
+def build_packed_gemm(desc, packed, bits_host, device, stream=None, into=None):
+    """Layout tables (numpy, from the per-channel bit-widths) + slq_build_packed_gemm_weights, written into the
+    persistent buffers ``into`` (or fresh ones).  Returns None when the kernel does not keep this layer's weights
+    resident (they are then streamed as u8 tiles) or the layer still has never-quantised rows."""
     lib = L.lib()
     bn_cols, n_tiles, k_block, num_kb, resident = conv_tiling(desc)
     if not resident or int(bits_host.max()) > 8:
         return None
     stream = L.current_stream() if stream is None else stream
+    pg = into if into is not None else alloc_packed_gemm(desc, device)
     rows = bn_cols * n_tiles
     bits = np.full(rows, 4, np.int64)
     bits[:len(bits_host)] = bits_host
@@ -111,16 +127,15 @@ def build_packed_gemm(desc, packed, bits_host, device, stream=None):
     seg_bytes = row_off[:, -1].astype(np.int32)
     tile_base = np.zeros(n_tiles, np.int64)
     tile_base[1:] = np.cumsum(num_kb * seg_bytes.astype(np.int64))[:-1]
-    total = int(num_kb * seg_bytes.astype(np.int64).sum())
-    assert row_off.max() < 65536
-    blob = torch.empty(max(total, 16), dtype=torch.uint8, device=device)
-    tb = torch.from_numpy(tile_base).to(device)
-    sb = torch.from_numpy(seg_bytes).to(device)
-    ro = torch.from_numpy(row_off.astype(np.uint16).view(np.int16)).to(device)
+    pg.used_bytes = int(num_kb * seg_bytes.astype(np.int64).sum())
+    assert row_off.max() < 65536 and pg.used_bytes <= pg.blob.numel()
+    pg.tile_base.copy_(torch.from_numpy(tile_base), non_blocking=False)
+    pg.seg_bytes.copy_(torch.from_numpy(seg_bytes), non_blocking=False)
+    pg.row_offsets.copy_(torch.from_numpy(row_off.astype(np.uint16).view(np.int16)), non_blocking=False)
     L.check(lib.slq_build_packed_gemm_weights(ctypes.byref(desc), packed.blob.data_ptr(), packed.offsets.data_ptr(),
-                                              packed.bits.data_ptr(), tb.data_ptr(), sb.data_ptr(), ro.data_ptr(),
-                                              blob.data_ptr(), stream))
-    return PackedGemm(blob, tb, sb, ro)
+                                              packed.bits.data_ptr(), pg.tile_base.data_ptr(), pg.seg_bytes.data_ptr(),
+                                              pg.row_offsets.data_ptr(), pg.blob.data_ptr(), stream))
+    return pg
 
 
 def encode_weight(w, bit, z, s, bits_host, stream=None):
@@ -219,16 +234,15 @@ class Engine:
         for op in self.ops:
             max_out = max(max_out, op.M * op.Cout)
         self.final_id, self.final_hw, self.final_c = x_id, h * w, self.act[x_id].shape[3]
-        # per-pixel channel sums ("rowsum") of every u8 activation that feeds a conv: ONE pool, zeroed by one
-        # memset at the start of a pass; producers accumulate into their slice, consumers gather their
-        # window sums from it (slq_epilogue.in_rowsum / out_rowsum)
+        # per-pixel channel sums ("rowsum") of every u8 activation that feeds a conv: a stack of planes per tensor
+        # (one per n-tile of the producing launch: at most Cout / 64); producers write their planes with plain
+        # stores, consumers add them over their window (slq_epilogue.in_rowsum / out_rowsum)
         feeds = sorted({op.in_id for op in self.ops})
-        pixels = {i: self.act[i].shape[0] * self.act[i].shape[1] * self.act[i].shape[2] for i in feeds}
-        self.rowsum_pool = torch.zeros(sum(pixels.values()), dtype=torch.int32, device=dev)
-        self.rowsum, pos = {}, 0
+        self.rowsum, self.rowsum_planes = {}, {}
         for i in feeds:
-            self.rowsum[i] = self.rowsum_pool[pos:pos + pixels[i]]
-            pos += pixels[i]
+            n_, h_, w_, c_ = self.act[i].shape
+            self.rowsum[i] = torch.zeros((max(c_ // 64, 1), n_ * h_ * w_), dtype=torch.int32, device=dev)
+            self.rowsum_planes[i] = 1
         self.f32_scratch = torch.empty(max_out, dtype=torch.float32, device=dev)
         self.act_scales = torch.ones(len(self.act), dtype=torch.float32, device=dev)
         self.absmax_tmp = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -331,19 +345,24 @@ class Engine:
                         h = ctypes.c_void_p()
                         L.check(lib.slq_conv_create(ctypes.byref(desc), self.act[op.in_id].data_ptr(),
                                                     wg.data_ptr(), ctypes.byref(h)))
-                        var = op.variants[w16] = (desc, wg, h)
-                    desc, wg, h = var
+                        pgbuf = None
+                        if w16 == 0 and self.packed_b and self.impl == L.IMPL_UMMA:
+                            # resident-weight layers take their B operand PACKED (<= 4-bit rows two codes per byte),
+                            # unpacked in shared memory; attached once, contents rewritten in place on every re-pack
+                            pgbuf = alloc_packed_gemm(desc, dev)
+                            if pgbuf is not None:
+                                L.check(lib.slq_conv_set_packed_weights(h, pgbuf.blob.data_ptr(), pgbuf.tile_base.data_ptr(),
+                                                                        pgbuf.seg_bytes.data_ptr(), pgbuf.row_offsets.data_ptr()))
+                        var = op.variants[w16] = (desc, wg, h, pgbuf)
+                    desc, wg, h, pgbuf = var
                     L.check(lib.slq_build_gemm_weights(ctypes.byref(desc), op.packed.blob.data_ptr(),
                                                        op.packed.offsets.data_ptr(), op.packed.bits.data_ptr(),
                                                        wg.data_ptr(), stream))
-                    # resident-weight layers take their B operand PACKED (4-bit rows two codes per byte), unpacked in
-                    # shared memory; the u8 matrix above stays the operand of the streamed layers and of the SIMT checker
-                    pg = build_packed_gemm(desc, op.packed, bits_host, dev, stream) if (self.packed_b and self.impl == L.IMPL_UMMA) else None
-                    L.check(lib.slq_conv_set_packed_weights(h, L.ptr(pg.blob if pg else None), L.ptr(pg.tile_base if pg else None),
-                                                            L.ptr(pg.seg_bytes if pg else None), L.ptr(pg.row_offsets if pg else None)))
-                    if (op.packed_gemm is None) != (pg is None) or op.w16 != w16:
-                        self._graphs, self._seen = {}, set()  # another kernel variant / other pointers: graphs are stale
-                    op.packed_gemm = pg
+                    if pgbuf is not None:
+                        build_packed_gemm(desc, op.packed, bits_host, dev, stream, into=pgbuf)
+                    if op.w16 != w16:  # one-limb <-> two-limb: another kernel variant, graphs are stale
+                        self._graphs, self._seen = {}, set()
+                    op.packed_gemm = pgbuf
                     op.handle, op.w16, op.desc, op.wg = h, w16, desc, wg
                     op.s_dev, op.z_dev = s, z
                     self._fold_into(op)
@@ -363,6 +382,20 @@ class Engine:
                                                    self.fc_w_split.data_ptr(), stream))
                 self.fc_b.copy_(self.net.fc.bias.detach())
                 self.ends_sig = ends_sig
+        # how many rowsum planes every producer writes (n-tiles of the tiling its launch uses): a layer that moved
+        # between the one-limb and two-limb modes changes it, and with it its consumers' epilogue descriptors
+        changed = False
+        for op in self.ops:
+            if op.out_id in self.rowsum and not op.signed:
+                planes = max(int(lib.slq_conv_rowsum_planes(op.handle, 1 if op.res_id >= 0 else 0)), 1)
+                if planes > self.rowsum[op.out_id].shape[0]:
+                    raise RuntimeError("rowsum planes: %d > %d allocated" % (planes, self.rowsum[op.out_id].shape[0]))
+                if self.rowsum_planes[op.out_id] != planes:
+                    self.rowsum_planes[op.out_id], changed = planes, True
+        if changed:
+            for op in self.ops:
+                op.epi = {}
+            self._graphs, self._seen = {}, set()
         self.weights_version += 1
         return len(todo)
 
@@ -386,10 +419,11 @@ class Engine:
         if e is None:
             res = self.act[op.res_id].data_ptr() if op.res_id >= 0 else None
             rs_out = self.rowsum.get(op.out_id) if mode == L.OUT_U8 else None
+            rs_in = self.rowsum[op.in_id]
             e = L.Epilogue(op.wscale.data_ptr(), op.zf.data_ptr(), op.bias.data_ptr(),
                            self.act_scales.data_ptr(), op.in_id, op.out_id, op.res_id, res,
                            1 if op.res_signed else 0, out_ptr, out_S, mode, 1 if op.relu else 0,
-                           self.rowsum[op.in_id].data_ptr(), L.ptr(rs_out))
+                           rs_in.data_ptr(), L.ptr(rs_out), self.rowsum_planes[op.in_id], rs_in.shape[1])
             op.epi[key] = e
         return e
 
@@ -438,7 +472,6 @@ class Engine:
                     torch.maximum(self.act_scales[idx:idx + 1], old[idx:idx + 1], out=self.act_scales[idx:idx + 1])
 
             n0 = self.act[0].numel()
-            self._zero_rowsums(st)
             self._stem(x.data_ptr(), f32.data_ptr(), L.OUT_F32, st)
             L.check(lib.slq_absmax_scale(f32.data_ptr(), n0, sc, 0, 255, tmp, st))
             settle(0)
@@ -483,7 +516,6 @@ class Engine:
     def launch_all(self, x_ptr, st):
         lib = self.lib
         sc = self.act_scales.data_ptr()
-        self._zero_rowsums(st)
         self._stem(x_ptr, self.act[0].data_ptr(), L.OUT_U8, st)
         for op in self.ops:
             mode = L.OUT_S8 if op.signed else L.OUT_U8
@@ -492,10 +524,7 @@ class Engine:
         L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
                                      sc, self.final_id, self.fc_w_split.data_ptr(), self.fc_b.data_ptr(),
                                      self.logits.shape[1], self.tail_ws.data_ptr(), self.logits.data_ptr(), st))
-        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 3  # + one memset node
-
-    def _zero_rowsums(self, st):
-        L.check(self.lib.slq_zero_async(self.rowsum_pool.data_ptr(), self.rowsum_pool.numel() * 4, st))
+        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 3
 
     def _stem(self, x_ptr, out_ptr, mode, st):
         lib, sc = self.lib, self.act_scales.data_ptr()
@@ -543,7 +572,7 @@ class Engine:
     def __del__(self):
         try:
             for op in getattr(self, "ops", []):
-                for _desc, _wg, h in getattr(op, "variants", {}).values():
+                for _desc, _wg, h, _pg in getattr(op, "variants", {}).values():
                     self.lib.slq_conv_destroy(h)
                 op.variants, op.handle = {}, None
             if getattr(self, "stem", None) is not None:

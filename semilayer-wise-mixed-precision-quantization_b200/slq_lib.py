@@ -31,7 +31,7 @@ class Epilogue(ctypes.Structure):
                 ("in_id", _i32), ("out_id", _i32), ("res_id", _i32),
                 ("res", _vp), ("res_signed", _i32),
                 ("out", _vp), ("out_S", _vp), ("out_mode", _i32), ("relu", _i32),
-                ("in_rowsum", _vp), ("out_rowsum", _vp)]
+                ("in_rowsum", _vp), ("out_rowsum", _vp), ("in_planes", _i32), ("in_plane_stride", _i64)]
 
 
 # name -> (restype, argtypes); mirrors include/slq.h one to one (tests check the export list)
@@ -59,7 +59,7 @@ SIGNATURES = {
     "slq_conv_launch": (ctypes.c_int, [_vp, ctypes.POINTER(Epilogue), _vp]),
     "slq_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
     "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
-    "slq_zero_async": (ctypes.c_int, [_vp, _i64, _vp]),
+    "slq_conv_rowsum_planes": (_i32, [_vp, _i32]),
     "slq_stem_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "slq_stem_create": (ctypes.c_int, [_i32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),
     "slq_stem_destroy": (None, [_vp]),

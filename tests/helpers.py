@@ -132,7 +132,7 @@ class ConvCase:
         out = torch.full((self.M, ncol), -7, dtype=torch.int32, device=self.device)
         S = torch.full((self.M,), -7, dtype=torch.int32, device=self.device)
         e = L.Epilogue(None, None, None, None, 0, 0, -1, None, 0, out.data_ptr(), S.data_ptr(), L.OUT_ACC, 0,
-                       self.rowsum.data_ptr(), None)
+                       self.rowsum.data_ptr(), None, 1, self.rowsum.numel())
         L.check(L.lib().slq_conv_launch(self.handle, ctypes.byref(e), L.current_stream()))
         torch.cuda.synchronize()
         return out.cpu().numpy(), S.cpu().numpy()
@@ -147,17 +147,20 @@ class ConvCase:
             out = torch.full((self.M, self.cout), float("nan"), dtype=torch.float32, device=dev)
         else:
             out = torch.full((self.M, self.cout), 77, dtype=torch.uint8, device=dev)
-        self.out_rowsum = torch.zeros(self.M, dtype=torch.int32, device=dev) if mode == L.OUT_U8 else None
+        planes = L.lib().slq_conv_rowsum_planes(self.handle, 1 if res is not None else 0)
+        self.out_rowsum = (torch.full((max(planes, 1), self.M), -3, dtype=torch.int32, device=dev)
+                           if mode == L.OUT_U8 else None)
         e = L.Epilogue(ws.data_ptr(), zz.data_ptr(), bb.data_ptr(), sc.data_ptr(), in_id, out_id, res_id,
                        L.ptr(rs), res_signed, out.data_ptr(), None, mode, relu, self.rowsum.data_ptr(),
-                       L.ptr(self.out_rowsum))
+                       L.ptr(self.out_rowsum), 1, self.rowsum.numel())
         L.check(L.lib().slq_conv_launch(self.handle, ctypes.byref(e), L.current_stream()))
         torch.cuda.synchronize()
         got = out.cpu().numpy()
         if self.out_rowsum is not None and self.desc.impl == L.IMPL_UMMA:
             # the side tensor the next layer's epilogue gathers its window sums from
+            # (one plane per n-tile of the launch; their sum is the channel sum of the pixel)
             want = got.astype(np.int64).sum(1)
-            assert np.array_equal(self.out_rowsum.cpu().numpy().astype(np.int64), want), "out_rowsum"
+            assert np.array_equal(self.out_rowsum.cpu().numpy().astype(np.int64).sum(0), want), "out_rowsum"
         return got
 
 

@@ -29,11 +29,11 @@ zz = torch.full((cout,), -120.0, device=dev)
 bb = torch.zeros(cout, device=dev)
 sc = torch.tensor([1.0, 0.05, 0.5, 1.0], device=dev)
 res = torch.randint(0, 256, (case.M, cout), dtype=torch.uint8, device=dev) if mode in ("res", "sres") else None
-rs_out = torch.zeros(case.M, dtype=torch.int32, device=dev)
+rs_out = torch.zeros((max(cout // 64, 1), case.M), dtype=torch.int32, device=dev)
 out_mode = L.OUT_S8 if mode == "w16" else L.OUT_U8
 e = L.Epilogue(ws.data_ptr(), zz.data_ptr(), bb.data_ptr(), sc.data_ptr(), 0, 1, 2 if res is not None else -1, L.ptr(res),
                1 if mode == "sres" else 0, out.data_ptr(), None, out_mode, 0 if mode == "w16" else 1,
-               case.rowsum.data_ptr(), rs_out.data_ptr() if out_mode == L.OUT_U8 else None)
+               case.rowsum.data_ptr(), rs_out.data_ptr() if out_mode == L.OUT_U8 else None, 1, case.rowsum.numel())
 best = 1e9
 for rep in range(8):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -27,7 +27,7 @@ ws = torch.ones(cout, device="cuda")
 zz = torch.zeros(cout, device="cuda")
 sc = torch.ones(4, device="cuda")
 e = L.Epilogue(ws.data_ptr(), zz.data_ptr(), zz.data_ptr(), sc.data_ptr(), 0, 1, -1, None, 0, out.data_ptr(), None,
-               L.OUT_U8, 1, case.rowsum.data_ptr(), None)
+               L.OUT_U8, 1, case.rowsum.data_ptr(), None, 1, case.rowsum.numel())
 for rep in range(3):
     buf.zero_()
     L.check(lib.slq_debug_set_trace(buf.data_ptr() if rep == 2 else None, -1))
