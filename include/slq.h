@@ -210,13 +210,13 @@ typedef struct slq_epilogue {
   int32_t *out_S;          /* SLQ_OUT_ACC only: [M] window sums, may be NULL                       */
   int32_t out_mode;
   int32_t relu;
-  /* Per-pixel channel sums ("rowsum") of u8 activations: the zero-point term z[oc] * S[m] needs the window sum
-   * S[m] of the INPUT; the tcgen05 kernel gathers it from side tensors instead of spending tensor work on a row
-   * of ones.  A side tensor is a stack of PLANES of one uint32 per pixel; the channel sum of a pixel is the sum
-   * of its planes (every n-tile of the producing launch writes its own plane with plain stores: no atomics,
-   * nothing to zero).                                                                                       */
-  const uint32_t *in_rowsum; /* [in_planes][in_plane_stride], in_plane_stride >= N*H*W pixels of the input
-                                (required by SLQ_IMPL_UMMA; the SIMT checker computes S itself and ignores it) */
+  /* Window sums S[m] of the INPUT for the zero-point term z[oc] * S[m].  Layers that run 64- / 128-channel tiles
+   * let the tensor core produce S (a row of ones behind the weight rows) and ignore these fields.  Layers that run
+   * 256-channel tiles (slq_conv_needs_rowsum) gather S from a ROWSUM side tensor of their input: a stack of PLANES of
+   * one uint32 per pixel whose sum is the channel sum of the pixel.  A producer whose output feeds such a layer is
+   * given out_rowsum and writes one plane per n-tile of its launch (plain stores: no atomics, nothing to zero).   */
+  const uint32_t *in_rowsum; /* [in_planes][in_plane_stride], in_plane_stride >= N*H*W pixels of the input; may be
+                                NULL unless slq_conv_needs_rowsum()                                            */
   uint32_t *out_rowsum;      /* SLQ_OUT_U8 only, may be NULL: [slq_conv_rowsum_planes()][M] planes of the output */
   int32_t in_planes;
   int64_t in_plane_stride;
@@ -231,6 +231,8 @@ SLQ_API int slq_debug_set_trace(int64_t *buf, int32_t capacity_events);
 /* Planes a launch of this layer writes into slq_epilogue.out_rowsum (= n-tiles of the tiling it will use, which
  * depends on whether the launch has a residual); 0 for the SIMT checker.                                  */
 SLQ_API int32_t slq_conv_rowsum_planes(const slq_conv *c, int32_t has_residual);
+/* 1 when a launch of this layer (with / without residual) gathers its window sums from slq_epilogue.in_rowsum. */
+SLQ_API int32_t slq_conv_needs_rowsum(const slq_conv *c, int32_t has_residual);
 
 /* y[m, oc] = (acc[m,oc] + z[oc] * S[m]) * wscale[oc] * act_scales[in_id] + bias[oc]
  *            (+ res[m,oc] * act_scales[res_id]) ; ReLU ; u8 = clamp(rint(y / act_scales[out_id])) */

@@ -7,13 +7,15 @@
 //   A = NHWC u8 activations, gathered by TMA: im2col-mode tensor map for 3x3 / strided layers
 //       (zero padding and the (r,s) filter offsets are resolved by the TMA unit), tiled map for
 //       1x1 stride-1 layers;  B = GEMM-ready weight codes [rows, K], K ordered (r, s, c).
-//   The zero-point correction z[oc]*S[m] needs the window sum S[m] = sum_k A[m, k]: every
-//   producer of a u8 activation also writes its per-pixel channel sums into a side tensor (rowsum: one PLANE
-//   of 4 bytes per pixel per n-tile of the producer -- one DP4A per four outputs, the two half-tile warps
-//   combine through shared memory, one coalesced 4-byte store per pixel and tile; atomics cost ~1.3 cycles per
-//   lane on the SM and were what the epilogue-bound layers then waited for), and the consumer's epilogue adds
-//   the planes over the <= 9 taps of its window, one tile ahead of the accumulator it is needed for.  (Round 1 appended a row of ones to every B tile
-//   instead: N = 144, 12.5 % more tensor work and no room for the N = 256 tiles below.)
+//   The zero-point correction z[oc]*S[m] needs the window sum S[m] = sum_k A[m, k].
+//   64- and 128-channel tiles let the tensor core produce it: a constant row of ones behind the B rows of every
+//   tile (UMMA N = bn + 16) puts S[m] into one more accumulator column.  The 256-channel tiles of the K-heavy
+//   layers have no column to spare (N = 256 is the largest UMMA): there the epilogue gathers S from a ROWSUM side
+//   tensor -- one plane of 4 bytes per pixel per n-tile of the producing launch (one DP4A per four outputs in the
+//   producer's epilogue, the two half-tile warps combine through shared memory, one coalesced store per pixel) --
+//   adding the planes over the <= 9 taps of its window one tile ahead.  Only the small late-stage tensors that
+//   feed such layers carry a rowsum; the gather's latency hides behind the long tiles of those layers (in the
+//   epilogue-bound early layers both the gather and atomics were measured to cost 10-30 %).
 //   K-heavy layers (weights streamed, Cout % 256 == 0) run 256-channel tiles: UMMA N = 256 is the shape at
 //   which one tcgen05.mma occupies the tensor pipe for as long as a warp needs to issue the next one
 //   (128 cycles, tools/issue_bench.cu), and a K block then moves 48 KB per 512 tensor cycles instead of
@@ -60,7 +62,7 @@ struct SmemPlan {
   int stage_bytes;   // stride between stages
   int group;         // K blocks per stage (1 when B is streamed)
   int a_bytes;       // kTileM * SWZ
-  int b_tile_bytes;  // bn_cols * SWZ
+  int b_tile_bytes;  // (bn_cols + 16 rows of the ones group when bn_cols < 256) * SWZ
   int b_resident;    // 1: B tiles at b_off + kb * b_tile_bytes ; 0: inside each stage after A
   int mma_warps;     // 2: warps 1 and 3 issue MMAs (1: warp 1 only; experiments)
   int b_off;
@@ -78,7 +80,7 @@ constexpr int kMaxGroup = 4;
 inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
   SmemPlan p{};
   p.a_bytes = kTileM * swz;
-  p.b_tile_bytes = g.bn_cols * swz;
+  p.b_tile_bytes = (g.bn_cols + (g.bn_cols < 256 ? 16 : 0)) * swz;
   const int num_kb = g.Ktot / swz;
   const long long b_all = (long long)num_kb * p.b_tile_bytes;
 #if SLQ_DEBUG_TRACE  // experiment knobs exist only in the debug build of the library
@@ -268,7 +270,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const ConvGeom &g = a.g;
   const EpiDev &e = a.e;
   const int bn_cols = g.bn_cols;
-  const int umma_n = bn_cols;
+  const bool ones_row = bn_cols < 256;  // S[m] from the tensor core (else from the rowsum side tensor)
+  const int umma_n = bn_cols + (ones_row ? 16 : 0);
   constexpr bool kWide = RES == kResWide;
   const bool has_res = RES == kResDyn ? (e.res != nullptr) : (RES != kResNone && RES != kResWide);
   const TileWalk walk(a);
@@ -309,6 +312,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // constant "ones" row group behind the B rows of every B tile:
+  // row bn_cols = 0x01.., rows bn_cols+1 .. +15 = 0  (identical bytes are swizzle-invariant)
+  if (ones_row) {
+    const int b_tiles = sp.b_resident ? a.num_kb : sp.stages;
+    const int b_stride = sp.b_resident ? sp.b_tile_bytes : sp.stage_bytes;
+    const int b_first = sp.b_resident ? sp.b_off : sp.a_bytes;
+    for (int i = threadIdx.x; i < b_tiles * 16 * (SWZ / 16); i += blockDim.x) {
+      const int t = i / (16 * (SWZ / 16));
+      const int rem = i % (16 * (SWZ / 16));
+      const int row = rem / (SWZ / 16), chunk = rem % (SWZ / 16);
+      uint4 v = row == 0 ? make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u) : make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4 *>(smem + b_first + t * b_stride + (bn_cols + row) * SWZ + chunk * 16) = v;
+    }
+  }
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -343,7 +360,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint8_t *src = a.wgp + a.wgp_tile[walk.my_n];
           mbar_expect_tx(bfull_bar, seg * (uint32_t)a.num_kb);
           for (int kb = 0; kb < a.num_kb; ++kb)
-            bulk_g2s(smem_base + sp.b_off + (kb + 1) * sp.b_tile_bytes - seg, src + (long long)kb * seg, seg, bfull_bar);
+            bulk_g2s(smem_base + sp.b_off + kb * sp.b_tile_bytes + bn_cols * SWZ - seg, src + (long long)kb * seg, seg, bfull_bar);
         } else {
           mbar_expect_tx(bfull_bar, b_bytes * (uint32_t)a.num_kb);
           for (int kb = 0; kb < a.num_kb; ++kb)
@@ -647,7 +664,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(bfull_bar, 0);
       for (int kb = 0; kb < a.num_kb; ++kb) {
         const uint32_t tile_s = smem_base + sp.b_off + kb * sp.b_tile_bytes;
-        const uint32_t raw_s = tile_s + sp.b_tile_bytes - seg;
+        const uint32_t raw_s = tile_s + (uint32_t)(bn_cols * SWZ) - seg;  // behind it: the ones group
         uint4 v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -677,7 +694,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_arrive(bready_bar);
     }
     uint32_t S_next = 0;
-    if (team < walk.count) {
+    if (!ones_row && team < walk.count) {
       int mt0, nt0;
       walk.at(team, mt0, nt0);
       S_next = window_sum(mt0 * kTileM + row);
@@ -704,8 +721,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // of tile it + 2 are in flight while tile it is converted), so their latency is never exposed
       const long long m = (long long)m_tile * kTileM + row;
       const bool valid = m < g.M;
-      const uint32_t S_raw = S_next;
-      if (it + 2 < walk.count) {
+      uint32_t S_raw = S_next;
+      if (!ones_row && it + 2 < walk.count) {
         int mt2, nt2;
         walk.at(it + 2, mt2, nt2);
         S_next = window_sum(mt2 * kTileM + row);
@@ -717,6 +734,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t rsb = smem_base + sp.res_off + rbuf * kOutTileBytes;
       if (has_res) mbar_wait(rfull_bar(rbuf), (uint32_t)((it / sp.res_bufs) & 1));
       const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * a.acc_stride;
+      if (ones_row) {
+        S_raw = tmem_ld1(trow + bn_cols);
+        tmem_ld_wait();
+      }
       const float Sf = (float)S_raw;  // <= 9 * 2048 * 255 < 2^24: exact
       uint32_t rsum = 0;              // channel sum of this thread's u8 outputs of the tile
       if (OUT == SLQ_OUT_ACC && e.out_S && valid && n_tile == 0 && half == 0) e.out_S[m] = (int)S_raw;
@@ -1140,8 +1161,11 @@ extern "C" int slq_conv_launch(slq_conv *c, const slq_epilogue *ep, void *stream
   e.Cout = c->g.Cout; e.w16 = c->g.w16; e.M = c->g.M;
   cudaStream_t st = (cudaStream_t)stream;
   if (c->desc.impl == SLQ_IMPL_SIMT) return launch_conv_simt(c->g, c->in, c->wg, e, st);
-  SLQ_CHECK_ARG(ep->in_rowsum != nullptr && ep->in_planes >= 1 && ep->in_plane_stride >= (int64_t)c->g.N * c->g.H * c->g.W,
-                "slq_conv_launch: in_rowsum (per-pixel channel sums of the input: planes, plane stride) missing");
+  const bool wide_launch = c->wide_ok && ep->res == nullptr && !c->g.w16;
+  SLQ_CHECK_ARG(!wide_launch || (ep->in_rowsum != nullptr && ep->in_planes >= 1 &&
+                                 ep->in_plane_stride >= (int64_t)c->g.N * c->g.H * c->g.W),
+                "slq_conv_launch: this layer runs 256-channel tiles and needs in_rowsum (per-pixel channel sums of its "
+                "input: planes, plane stride; slq_conv_needs_rowsum)");
   const int tma_out = (ep->out_mode == SLQ_OUT_U8 || ep->out_mode == SLQ_OUT_S8) ? 1 : 0;
   if (tma_out && c->out_ptr != ep->out) {  // (re)encode the store map for this output buffer
     int rc = encode_out_map(&c->tmO, ep->out, c->g, "out");
@@ -1183,6 +1207,11 @@ extern "C" int slq_conv_set_packed_weights(slq_conv *c, const uint8_t *wgp, cons
   c->wgp_seg = seg_bytes;
   c->wgp_rowoff = row_offsets;
   return SLQ_OK;
+}
+
+extern "C" int32_t slq_conv_needs_rowsum(const slq_conv *c, int32_t has_residual) {
+  if (!c || c->desc.impl != SLQ_IMPL_UMMA) return 0;
+  return (c->wide_ok && !has_residual && !c->g.w16) ? 1 : 0;
 }
 
 extern "C" int32_t slq_conv_rowsum_planes(const slq_conv *c, int32_t has_residual) {

@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     const int pt = threadIdx.x - (1 + kTsBuildW + kTsMmaW + kTsEpiW) * 32;  // 0..127
     const uint8_t *cring = smem + kTsConvOff;
     int ve = 0;
-    if (a.out_mode != SLQ_OUT_F32) {
+    if (a.out_mode != SLQ_OUT_F32 && !(SF_DBG(a) & 4)) {  // (debug bit 4: the epilogue emits nothing)
       for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
         int n, j0, j1, p0, p1;
         unit_rows(a, u, n, j0, j1, p0, p1);

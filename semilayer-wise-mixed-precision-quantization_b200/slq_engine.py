@@ -234,15 +234,10 @@ class Engine:
         for op in self.ops:
             max_out = max(max_out, op.M * op.Cout)
         self.final_id, self.final_hw, self.final_c = x_id, h * w, self.act[x_id].shape[3]
-        # per-pixel channel sums ("rowsum") of every u8 activation that feeds a conv: a stack of planes per tensor
-        # (one per n-tile of the producing launch: at most Cout / 64); producers write their planes with plain
-        # stores, consumers add them over their window (slq_epilogue.in_rowsum / out_rowsum)
-        feeds = sorted({op.in_id for op in self.ops})
+        # per-pixel channel sums ("rowsum") of the u8 activations that feed a layer running 256-channel tiles (the
+        # K-heavy layers gather their window sums from it; everything else gets them from the tensor core): a stack
+        # of planes per tensor, one per n-tile of the producing launch.  Allocated when a consumer first needs it.
         self.rowsum, self.rowsum_planes = {}, {}
-        for i in feeds:
-            n_, h_, w_, c_ = self.act[i].shape
-            self.rowsum[i] = torch.zeros((max(c_ // 64, 1), n_ * h_ * w_), dtype=torch.int32, device=dev)
-            self.rowsum_planes[i] = 1
         self.f32_scratch = torch.empty(max_out, dtype=torch.float32, device=dev)
         self.act_scales = torch.ones(len(self.act), dtype=torch.float32, device=dev)
         self.absmax_tmp = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -382,16 +377,24 @@ class Engine:
                                                    self.fc_w_split.data_ptr(), stream))
                 self.fc_b.copy_(self.net.fc.bias.detach())
                 self.ends_sig = ends_sig
-        # how many rowsum planes every producer writes (n-tiles of the tiling its launch uses): a layer that moved
-        # between the one-limb and two-limb modes changes it, and with it its consumers' epilogue descriptors
-        changed = False
+        # which activations need a rowsum side tensor (their consumer runs 256-channel tiles) and how many planes the
+        # producer writes (n-tiles of the tiling its launch uses).  A layer that moved between the two-limb and the
+        # one-limb mode changes both, and with them the epilogue descriptors of its neighbours.
+        need = {op.in_id for op in self.ops if lib.slq_conv_needs_rowsum(op.handle, 1 if op.res_id >= 0 else 0)}
+        planes = {0: 1}
         for op in self.ops:
-            if op.out_id in self.rowsum and not op.signed:
-                planes = max(int(lib.slq_conv_rowsum_planes(op.handle, 1 if op.res_id >= 0 else 0)), 1)
-                if planes > self.rowsum[op.out_id].shape[0]:
-                    raise RuntimeError("rowsum planes: %d > %d allocated" % (planes, self.rowsum[op.out_id].shape[0]))
-                if self.rowsum_planes[op.out_id] != planes:
-                    self.rowsum_planes[op.out_id], changed = planes, True
+            if not op.signed:
+                planes[op.out_id] = max(int(lib.slq_conv_rowsum_planes(op.handle, 1 if op.res_id >= 0 else 0)), 1)
+        changed = set(self.rowsum) != need
+        for i in need:
+            if i not in self.rowsum:
+                n_, h_, w_, c_ = self.act[i].shape
+                self.rowsum[i] = torch.zeros((max(c_ // 64, 1), n_ * h_ * w_), dtype=torch.int32, device=dev)
+            if self.rowsum_planes.get(i) != planes[i]:
+                self.rowsum_planes[i], changed = planes[i], True
+        for i in [i for i in self.rowsum if i not in need]:
+            del self.rowsum[i]
+            self.rowsum_planes.pop(i, None)
         if changed:
             for op in self.ops:
                 op.epi = {}
@@ -419,11 +422,12 @@ class Engine:
         if e is None:
             res = self.act[op.res_id].data_ptr() if op.res_id >= 0 else None
             rs_out = self.rowsum.get(op.out_id) if mode == L.OUT_U8 else None
-            rs_in = self.rowsum[op.in_id]
+            rs_in = self.rowsum.get(op.in_id)
             e = L.Epilogue(op.wscale.data_ptr(), op.zf.data_ptr(), op.bias.data_ptr(),
                            self.act_scales.data_ptr(), op.in_id, op.out_id, op.res_id, res,
                            1 if op.res_signed else 0, out_ptr, out_S, mode, 1 if op.relu else 0,
-                           rs_in.data_ptr(), L.ptr(rs_out), self.rowsum_planes[op.in_id], rs_in.shape[1])
+                           L.ptr(rs_in), L.ptr(rs_out), self.rowsum_planes.get(op.in_id, 0),
+                           rs_in.shape[1] if rs_in is not None else 0)
             op.epi[key] = e
         return e
 
@@ -533,11 +537,11 @@ class Engine:
             norm = ctypes.cast(self.norm, ctypes.c_void_p) if kind == L.IN_U8 else None
             L.check(lib.slq_stem_launch_in(self.stem, x_ptr, kind, norm, self.stem_a.data_ptr(), self.stem_b.data_ptr(),
                                            sc, 0, out_ptr, mode, self.stem_scratch.data_ptr(),
-                                           self.rowsum[0].data_ptr(), st))
+                                           L.ptr(self.rowsum.get(0)), st))
         else:
             L.check(lib.slq_stem_forward(x_ptr, self.N, self.H, self.W, self.stem_w.data_ptr(),
                                          self.stem_a.data_ptr(), self.stem_b.data_ptr(), sc, 0,
-                                         self.stem_scratch.data_ptr(), out_ptr, mode, self.rowsum[0].data_ptr(), st))
+                                         self.stem_scratch.data_ptr(), out_ptr, mode, L.ptr(self.rowsum.get(0)), st))
 
     # ------------------------------------------------------------------------------------------
     def capture_graph(self, x_static):

@@ -60,6 +60,7 @@ SIGNATURES = {
     "slq_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
     "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "slq_conv_rowsum_planes": (_i32, [_vp, _i32]),
+    "slq_conv_needs_rowsum": (_i32, [_vp, _i32]),
     "slq_stem_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "slq_stem_create": (ctypes.c_int, [_i32, _i32, _i32, _vp, ctypes.POINTER(_vp)]),
     "slq_stem_destroy": (None, [_vp]),
