@@ -266,6 +266,8 @@ def main():
     ap.add_argument("--layers", default="", help="write the per-layer CUDA-event table to this file")
     ap.add_argument("--no-packed-b", action="store_true",
                     help="A/B: resident-weight layers take u8 weight tiles through TMA instead of packed codes unpacked in smem")
+    ap.add_argument("--no-fuse-tail", action="store_true",
+                    help="A/B: downsample conv and conv3 of a stage's first block as two launches (identity through HBM)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -344,7 +346,7 @@ def main():
     x = torch.randn(B, 3, 224, 224, generator=g, device=dev)
     x_host = x.cpu().pin_memory()
     impl = L.IMPL_SIMT if args.simt else L.IMPL_UMMA
-    eng = net.slq_engine(x, impl=impl, packed_b=not args.no_packed_b)
+    eng = net.slq_engine(x, impl=impl, packed_b=not args.no_packed_b, fuse_tail=not args.no_fuse_tail)
     eng.refresh_weights()
     eng.calibrate(x)
     eng.epoch = resnet.WEIGHT_EPOCH[0]
@@ -504,35 +506,30 @@ def main():
     # ---- roofline of the dominant kernel (conv_umma_kernel), timed live per launch -------------
     peaks = load_peaks()
     conv_ms, conv_ops, conv_bytes = 0.0, 0.0, 0.0
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in eng.ops]
-    import ctypes
+    sched = list(eng.schedule)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in sched]
     torch.cuda.synchronize()
     for rep in range(3):
-        for (a, b), op in zip(ev, eng.ops):
-            mode = L.OUT_S8 if op.signed else L.OUT_U8
-            e = eng._epilogue(op, mode, eng.act[op.out_id].data_ptr())
+        for (a, b), item in zip(ev, sched):
             a.record(st)
-            L.check(eng.lib.slq_conv_launch(op.handle, ctypes.byref(e), st.cuda_stream))
+            eng.launch_item(item, st.cuda_stream)
             b.record(st)
         torch.cuda.synchronize()
     per_layer = []
-    for (a, b), op in zip(ev, eng.ops):
+    for (a, b), item in zip(ev, sched):
         t = a.elapsed_time(b)
-        ops = 2.0 * op.M * op.Cout * op.k * op.k * op.Cin
-        byts = op.N_in_bytes if hasattr(op, "N_in_bytes") else (
-            eng.act[op.in_id].numel() + eng.act[op.out_id].numel() + op.wg.numel() +
-            (eng.act[op.res_id].numel() if op.res_id >= 0 else 0))
+        info = eng.item_info(item)
         conv_ms += t
-        conv_ops += ops
-        conv_bytes += byts
-        per_layer.append((t, ops, byts))
+        conv_ops += info["ops"]
+        conv_bytes += info["bytes"]
+        per_layer.append((t, info))
     if args.layers and rank == 0:
         with open(args.layers, "w") as f:
-            f.write("idx Cin Cout k s H M w16 res  us  TOPS  GB/s\n")
-            for i, ((t, ops, byts), op) in enumerate(zip(per_layer, eng.ops)):
-                f.write("%2d %4d %4d %d %d %3d %7d %d %d  %7.1f %7.1f %7.1f\n" % (
-                    i, op.Cin, op.Cout, op.k, op.stride, op.H, op.M, op.w16, 1 if op.res_id >= 0 else 0,
-                    1e3 * t, ops / (t * 1e-3) / 1e12, byts / (t * 1e-3) / 1e9))
+            f.write("idx kind Cin Cmid Cout k s H M w16 res  us  TOPS  GB/s\n")
+            for i, (t, d) in enumerate(per_layer):
+                f.write("%2d %s %4d %4d %4d %d %d %3d %7d %d %d  %7.1f %7.1f %7.1f\n" % (
+                    i, d["kind"], d["Cin"], d["Cmid"], d["Cout"], d["k"], d["stride"], d["H"], d["M"], d["w16"], d["res"],
+                    1e3 * t, d["ops"] / (t * 1e-3) / 1e12, d["bytes"] / (t * 1e-3) / 1e9))
     achieved_tops = conv_ops / (conv_ms * 1e-3) / 1e12
     i8 = measure_i8_peak(eng.lib, L, st, torch)
     # the conv launches above are timed one by one, in isolation (a few ms in total): the BURST figure applies
@@ -545,15 +542,16 @@ def main():
         prof = os.path.join(ROOT, "profiles", "r1_ncu_full_step_summary.csv")
     if args.arch == "resnet50" and B == 256 and os.path.exists(prof):
         import csv
-        rows = [r for r in csv.DictReader(open(prof)) if "conv_umma" in r["kernel"]]
-        if len(rows) == len(eng.ops):
+        rows = [r for r in csv.DictReader(open(prof)) if "conv_umma" in r["kernel"] or "block_tail" in r["kernel"]]
+        if len(rows) == len(sched):
             traffic = 1e6 * sum(float(r["dram_rd_MB"]) + float(r["dram_wr_MB"]) for r in rows) / len(rows)
     roofline = {"bound": "tensor", "achieved": achieved_tops, "peak": int8_peak, "unit": "TFLOP/s",
                 "frac": achieved_tops / int8_peak, "traffic": traffic,
                 "traffic_note": "mean DRAM bytes (read+write) per conv launch, %s; "
-                                "algorithmic mean %.1f MB" % (os.path.relpath(prof, ROOT), conv_bytes / len(eng.ops) / 1e6),
-                "kernel": "conv_umma_kernel: the %d conv launches of a step, each timed with CUDA events on the "
-                          "launching stream; achieved = sum(2*MAC) / sum(duration)" % len(eng.ops),
+                                "algorithmic mean %.1f MB" % (os.path.relpath(prof, ROOT), conv_bytes / len(sched) / 1e6),
+                "kernel": "conv_umma_kernel / block_tail_kernel: the %d conv launches of a step (%d of them fused block "
+                          "tails = downsample conv + conv3), each timed with CUDA events on the launching stream; "
+                          "achieved = sum(2*MAC) / sum(duration)" % (len(sched), sum(1 for k, _ in sched if k == "tail")),
                 "peak_source": "measured i8: slq_probe_i8_peak on this GPU in this run, burst (best of 5 x ~20 ms); "
                                "sustained over %.1f s: %.0f TOPS" % (i8["sustained_seconds"], i8["sustained_tops"]),
                 "peak_sustained": i8["sustained_tops"], "frac_vs_sustained_i8": achieved_tops / i8["sustained_tops"],

@@ -238,6 +238,51 @@ SLQ_API int32_t slq_conv_needs_rowsum(const slq_conv *c, int32_t has_residual);
  *            (+ res[m,oc] * act_scales[res_id]) ; ReLU ; u8 = clamp(rint(y / act_scales[out_id])) */
 SLQ_API int slq_conv_launch(slq_conv *c, const slq_epilogue *e, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * 2b. Tail of a residual block WITH a downsample branch as one launch
+ *     replaces  resnet.py:107-114 (Bottleneck.forward): out = bn3(conv3(y2)); identity = downsample(x) =
+ *               bn_d(conv1x1_stride_s(x)); out += identity; out = relu(out)
+ * Both 1x1 GEMMs of a 128-pixel x 64-channel tile accumulate side by side in tensor memory (conv3: u8 x u8 codes;
+ * downsample: u8 x two u8 limbs of its 16-bit codes, the reference keeps these weights in fp32) and ONE epilogue
+ * folds them, so the identity tensor never exists in HBM and is never rounded to 8 bits:
+ *   per channel : A3 = wscale3*s[in3_id] ; Ad = wscaled*s[ind_id] ; B = bias3 + biasd     (u8 out: each * 1/s[out_id])
+ *                 Z3 = zf3*A3 ; Zd = zfd*Ad
+ *   per element : accd = fma(f32(hi), 256, f32(lo))
+ *                 y = fma(accd, Ad, fma(f32(acc3), A3, fma(f32(Sd), Zd, fma(f32(S3), Z3, B))))
+ *   fp32 out    : max(y, 0)          u8 out : sat_u8(rint(y))
+ * (oracle/slq_oracle.py `block_tail` / `block_tail_q` restate it).  The kernel keeps the weights of one 64-channel
+ * n-tile of BOTH convs resident in shared memory: slq_blocktail_create returns SLQ_ERR_UNSUPPORTED when they do
+ * not fit (Cmid = 512 / Cin = 1024, the last stage of ResNet-50) -- the caller then launches the two convs
+ * separately (slq_conv_launch with the downsample output as s8 residual).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct slq_blocktail_desc {
+  int32_t N, H, W, Cin; /* block input x: u8 NHWC [N, H, W, Cin]                                        */
+  int32_t stride;       /* of the downsample conv (1 or 2); outputs are Ho = (H-1)/stride + 1 pixels     */
+  int32_t Cmid;         /* channels of y2 = conv3's input: u8 NHWC [N, Ho, Wo, Cmid]                     */
+  int32_t Cout;         /* output channels of both convs                                                 */
+  int32_t impl;         /* SLQ_IMPL_UMMA, or SLQ_IMPL_SIMT: the dp4a checker of the same arithmetic      */
+} slq_blocktail_desc;
+
+typedef struct slq_blocktail slq_blocktail; /* opaque */
+
+typedef struct slq_blocktail_epilogue {
+  const float *wscale3, *zf3, *bias3; /* conv3 + bn3, as in slq_epilogue                                 */
+  const float *wscaled, *zfd, *biasd; /* downsample conv + its BN                                        */
+  const float *act_scales;
+  int32_t in3_id, ind_id, out_id;     /* scales of y2, of x and of the output                            */
+  void *out;                          /* [M, Cout] u8 (SLQ_OUT_U8) or fp32 (SLQ_OUT_F32)                 */
+  int32_t out_mode;
+  uint32_t *out_rowsum;               /* SLQ_OUT_U8, may be NULL: [slq_blocktail_rowsum_planes()][M]      */
+} slq_blocktail_epilogue;
+
+/* y2, x: the two input activations; wg3: GEMM-ready weights of conv3 built with w16 = 0, wgd: of the downsample conv
+ * built with w16 = 1 (slq_build_gemm_weights).  All four are device pointers the handle keeps.            */
+SLQ_API int slq_blocktail_create(const slq_blocktail_desc *d, const uint8_t *y2, const uint8_t *x, const uint8_t *wg3,
+                                 const uint8_t *wgd, slq_blocktail **out);
+SLQ_API void slq_blocktail_destroy(slq_blocktail *h);
+SLQ_API int32_t slq_blocktail_rowsum_planes(const slq_blocktail *h);
+SLQ_API int slq_blocktail_launch(slq_blocktail *h, const slq_blocktail_epilogue *e, void *stream);
+
 /* =============================================================================================
  * 3. Un-quantised ends of the network and calibration helpers
  * ============================================================================================= */

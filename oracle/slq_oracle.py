@@ -258,6 +258,42 @@ def epilogue_q(acc, S, zf, wscale, bias, s_in, s_out, res_u8=None, s_res=None, a
     return np.clip(q, 0, 255).astype(np.uint8)
 
 
+def _block_tail_core(acc3, S3, zf3, wscale3, bias3, s_y2, lo, hi, Sd, zfd, wscaled, biasd, s_x, inv_out):
+    f = np.float32
+    a3 = (wscale3.astype(f) * f(s_y2)).astype(f)
+    ad = (wscaled.astype(f) * f(s_x)).astype(f)
+    b = (bias3.astype(f) + biasd.astype(f)).astype(f)
+    if inv_out is not None:
+        inv = f(inv_out)
+        a3, ad, b = (a3 * inv).astype(f), (ad * inv).astype(f), (b * inv).astype(f)
+    z3 = (zf3.astype(f) * a3).astype(f)
+    zd = (zfd.astype(f) * ad).astype(f)
+    accd = fma32(hi.astype(f), f(256.0), lo.astype(f))
+    y = fma32(S3.astype(f)[:, None], z3[None, :], b[None, :])
+    y = fma32(Sd.astype(f)[:, None], zd[None, :], y)
+    y = fma32(acc3.astype(f), a3[None, :], y)
+    return fma32(accd, ad[None, :], y)
+
+
+def block_tail(acc3, S3, zf3, wscale3, bias3, s_y2, lo, hi, Sd, zfd, wscaled, biasd, s_x):
+    """fp32 output of the fused block tail (csrc/block_tail.cu; include/slq.h section 2b), i.e. reference
+    resnet.py:107-114  relu(bn3(conv3(y2)) + bn_d(conv_d(x)))  on integer accumulators:
+         A3 = wscale3*s_y2 ; Ad = wscaled*s_x ; B = bias3 + biasd ; Z3 = zf3*A3 ; Zd = zfd*Ad
+         y = fma(fma(hi, 256, lo), Ad, fma(acc3, A3, fma(Sd, Zd, fma(S3, Z3, B)))) ; max(y, 0)
+    acc3 [M, Cout], S3 [M]: conv3 accumulators / window sums; lo, hi [M, Cout], Sd [M]: the two limbs of the
+    downsample conv's 16-bit codes and its window sums."""
+    y = _block_tail_core(acc3, S3, zf3, wscale3, bias3, s_y2, lo, hi, Sd, zfd, wscaled, biasd, s_x, None)
+    return np.maximum(y, np.float32(0))
+
+
+def block_tail_q(acc3, S3, zf3, wscale3, bias3, s_y2, lo, hi, Sd, zfd, wscaled, biasd, s_x, s_out):
+    """u8 output of the fused block tail: the same chain with inv = 1/s_out folded into A3, Ad and B BEFORE the
+    zero-point constants are formed, then sat_u8(rint(y))."""
+    inv = np.float32(1.0) / np.float32(s_out)
+    y = _block_tail_core(acc3, S3, zf3, wscale3, bias3, s_y2, lo, hi, Sd, zfd, wscaled, biasd, s_x, inv)
+    return np.clip(np.nan_to_num(np.rint(y), nan=0.0), 0, 255).astype(np.uint8)
+
+
 def requant_u8(y, s_out):
     """cvt.rni.sat.u8.f32(y * (1/s_out))"""
     inv = np.float32(1.0) / np.float32(s_out)

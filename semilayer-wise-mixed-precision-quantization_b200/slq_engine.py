@@ -3,7 +3,8 @@ static sequence of kernel launches over the C ABI (slq_lib) and runs it.
 
 Data layout in HBM:
   * activations: u8 NHWC per tensor, one static fp32 scale per tensor in ``act_scales`` (device
-    array); the downsample branch (not post-ReLU) is s8;
+    array); a downsample branch that runs as its own launch (not post-ReLU) is s8 -- in the Bottleneck
+    stages whose weights fit, it is fused into the block's conv3 launch and never exists in HBM;
   * weights: per conv a PackedLayer (bit/z/s32 per output channel + packed 2/4/8/16-bit codes) and
     the GEMM-ready u8 matrix the tcgen05 kernel streams with TMA;
   * everything is allocated once per (batch, H, W); a forward is launches only (CUDA-graph safe).
@@ -154,14 +155,25 @@ class _ConvOp:
     pass
 
 
+class _BlockTail:
+    """conv3 + downsample conv of one Bottleneck (resnet.py:107-114) that can run as ONE launch
+    (include/slq.h section 2b) while conv3 is quantised (<= 8-bit codes) and the downsample conv is not."""
+
+    def __init__(self, dop, op3):
+        self.dop, self.op3 = dop, op3
+        self.handle, self.unsupported, self.fused, self.epi = None, False, False, {}
+
+
 class Engine:
-    def __init__(self, net, N, H, W, device, impl=L.IMPL_UMMA, a_mode=L.A_AUTO, stem="umma", packed_b=True):
+    def __init__(self, net, N, H, W, device, impl=L.IMPL_UMMA, a_mode=L.A_AUTO, stem="umma", packed_b=True,
+                 fuse_tail=True):
         if device.type != "cuda":
             raise RuntimeError("slq Engine needs a CUDA device")
         self.lib = L.lib()
         self.net, self.N, self.H, self.W, self.device = net, N, H, W, device
         self.impl, self.a_mode = impl, a_mode
         self.packed_b = packed_b  # resident-weight layers fetch PACKED codes and unpack them in shared memory
+        self.fuse_tail = fuse_tail  # conv3 + downsample conv of a stage's first block as one launch
         self.stem_kind = stem  # "umma": tcgen05 fp16 stem; "simt": exact-fp32 CUDA-core stem
         self.stem = None
         self.epoch = -1
@@ -199,7 +211,7 @@ class Engine:
             raise RuntimeError("model parameters must live on the CUDA device (call net.to(device))")
         Hc, Wc = (self.H + 6 - 7) // 2 + 1, (self.W + 6 - 7) // 2 + 1
         Hp, Wp = (Hc + 2 - 3) // 2 + 1, (Wc + 2 - 3) // 2 + 1
-        self.act, self.act_signed, self.ops = [], [], []
+        self.act, self.act_signed, self.ops, self.tails, self.schedule = [], [], [], [], []
         self.stem_scratch = torch.empty(N * Hc * Wc * 64, dtype=torch.float32, device=dev)
         if self.stem_kind == "umma" and Wc > 128:
             self.stem_kind = "simt"  # one output row per 128-pixel tile: inputs wider than 256 px
@@ -227,6 +239,8 @@ class Engine:
                     dop = self._make_op(blk.downsample[0], blk.downsample[1], x_id, h, w, relu=False, signed=True)
                     res_id, res_signed = dop.out_id, True
                     pending.insert(len(pending) - 1, dop)
+                    if len(convs) == 3 and pending[-1].k == 1 and dop.k == 1:
+                        self.tails.append(_BlockTail(dop, pending[-1]))
                 last = pending[-1]
                 last.res_id, last.res_signed = res_id, res_signed
                 self.ops += pending
@@ -377,15 +391,44 @@ class Engine:
                                                    self.fc_w_split.data_ptr(), stream))
                 self.fc_b.copy_(self.net.fc.bias.detach())
                 self.ends_sig = ends_sig
+        # the launch schedule: a block tail whose conv3 is quantised and whose downsample conv is not runs fused
+        changed = False
+        for bt in self.tails:
+            want = self.fuse_tail and bt.op3.w16 == 0 and bt.dop.w16 == 1 and not bt.unsupported
+            if want and bt.handle is None:
+                dop, op3 = bt.dop, bt.op3
+                desc = L.BlockTailDesc(self.N, dop.H, dop.W, dop.Cin, dop.stride, op3.Cin, op3.Cout, self.impl)
+                h = ctypes.c_void_p()
+                rc = lib.slq_blocktail_create(ctypes.byref(desc), self.act[op3.in_id].data_ptr(),
+                                              self.act[dop.in_id].data_ptr(), op3.variants[0][1].data_ptr(),
+                                              dop.variants[1][1].data_ptr(), ctypes.byref(h))
+                if rc == L.SLQ_ERR_UNSUPPORTED:  # the two weight tiles do not fit one CTA: two launches
+                    bt.unsupported, want = True, False
+                else:
+                    L.check(rc)
+                    bt.handle = h
+            if want != bt.fused:
+                bt.fused, changed = want, True
+        inside = {id(o): bt for bt in self.tails if bt.fused for o in (bt.dop, bt.op3)}
+        self.schedule = []
+        for op in self.ops:
+            bt = inside.get(id(op))
+            if bt is None:
+                self.schedule.append(("conv", op))
+            elif op is bt.op3:
+                self.schedule.append(("tail", bt))
         # which activations need a rowsum side tensor (their consumer runs 256-channel tiles) and how many planes the
         # producer writes (n-tiles of the tiling its launch uses).  A layer that moved between the two-limb and the
         # one-limb mode changes both, and with them the epilogue descriptors of its neighbours.
-        need = {op.in_id for op in self.ops if lib.slq_conv_needs_rowsum(op.handle, 1 if op.res_id >= 0 else 0)}
+        need = {op.in_id for kind, op in self.schedule if kind == "conv"
+                and lib.slq_conv_needs_rowsum(op.handle, 1 if op.res_id >= 0 else 0)}
         planes = {0: 1}
-        for op in self.ops:
-            if not op.signed:
-                planes[op.out_id] = max(int(lib.slq_conv_rowsum_planes(op.handle, 1 if op.res_id >= 0 else 0)), 1)
-        changed = set(self.rowsum) != need
+        for kind, it in self.schedule:
+            if kind == "tail":
+                planes[it.op3.out_id] = max(int(lib.slq_blocktail_rowsum_planes(it.handle)), 1)
+            elif not it.signed:
+                planes[it.out_id] = max(int(lib.slq_conv_rowsum_planes(it.handle, 1 if it.res_id >= 0 else 0)), 1)
+        changed = changed or set(self.rowsum) != need
         for i in need:
             if i not in self.rowsum:
                 n_, h_, w_, c_ = self.act[i].shape
@@ -398,6 +441,8 @@ class Engine:
         if changed:
             for op in self.ops:
                 op.epi = {}
+            for bt in self.tails:
+                bt.epi = {}
             self._graphs, self._seen = {}, set()
         self.weights_version += 1
         return len(todo)
@@ -430,6 +475,45 @@ class Engine:
                            rs_in.shape[1] if rs_in is not None else 0)
             op.epi[key] = e
         return e
+
+    def _tail_epilogue(self, bt, mode, out_ptr):
+        key = (mode, out_ptr)
+        e = bt.epi.get(key)
+        if e is None:
+            o3, od = bt.op3, bt.dop
+            rs_out = self.rowsum.get(o3.out_id) if mode == L.OUT_U8 else None
+            e = L.BlockTailEpilogue(o3.wscale.data_ptr(), o3.zf.data_ptr(), o3.bias.data_ptr(),
+                                    od.wscale.data_ptr(), od.zf.data_ptr(), od.bias.data_ptr(),
+                                    self.act_scales.data_ptr(), o3.in_id, od.in_id, o3.out_id, out_ptr, mode,
+                                    L.ptr(rs_out))
+            bt.epi[key] = e
+        return e
+
+    def launch_item(self, item, st, mode=None, out_ptr=None):
+        """One entry of the launch schedule: ("conv", layer) or ("tail", fused block tail)."""
+        kind, it = item
+        if kind == "tail":
+            mode = L.OUT_U8 if mode is None else mode
+            out_ptr = self.act[it.op3.out_id].data_ptr() if out_ptr is None else out_ptr
+            L.check(self.lib.slq_blocktail_launch(it.handle, ctypes.byref(self._tail_epilogue(it, mode, out_ptr)), st))
+        else:
+            mode = (L.OUT_S8 if it.signed else L.OUT_U8) if mode is None else mode
+            out_ptr = self.act[it.out_id].data_ptr() if out_ptr is None else out_ptr
+            L.check(self.lib.slq_conv_launch(it.handle, ctypes.byref(self._epilogue(it, mode, out_ptr)), st))
+
+    def item_info(self, item):
+        """Shape, arithmetic and algorithmic HBM bytes of one schedule entry (bench / tools)."""
+        kind, it = item
+        if kind == "tail":
+            o3, od = it.op3, it.dop
+            return dict(kind="tail", Cin=od.Cin, Cmid=o3.Cin, Cout=o3.Cout, k=1, stride=od.stride, H=od.H, M=o3.M,
+                        w16=1, res=0, ops=2.0 * o3.M * o3.Cout * (o3.Cin + od.Cin),
+                        bytes=self.act[o3.in_id].numel() + self.act[od.in_id].numel() + self.act[o3.out_id].numel()
+                        + o3.wg.numel() + od.wg.numel())
+        return dict(kind="conv", Cin=it.Cin, Cmid=0, Cout=it.Cout, k=it.k, stride=it.stride, H=it.H, M=it.M,
+                    w16=it.w16, res=1 if it.res_id >= 0 else 0, ops=2.0 * it.M * it.Cout * it.k * it.k * it.Cin,
+                    bytes=self.act[it.in_id].numel() + self.act[it.out_id].numel() + it.wg.numel()
+                    + (self.act[it.res_id].numel() if it.res_id >= 0 else 0))
 
     # ------------------------------------------------------------------------------------------
     IN_KINDS = {torch.float32: L.IN_F32, torch.float16: L.IN_F16, torch.uint8: L.IN_U8}
@@ -480,14 +564,20 @@ class Engine:
             L.check(lib.slq_absmax_scale(f32.data_ptr(), n0, sc, 0, 255, tmp, st))
             settle(0)
             self._stem(x.data_ptr(), self.act[0].data_ptr(), L.OUT_U8, st)
-            for op in self.ops:
-                n = op.M * op.Cout
-                L.check(lib.slq_conv_launch(op.handle, ctypes.byref(self._epilogue(op, L.OUT_F32, f32.data_ptr())), st))
-                L.check(lib.slq_absmax_scale(f32.data_ptr(), n, sc, op.out_id, 127 if op.signed else 255, tmp, st))
+            for item in self.schedule:
+                op = item[1].op3 if item[0] == "tail" else item[1]   # the layer whose output tensor this writes
+                if item[0] == "tail":
+                    # the identity tensor does not exist on this path; its scale is still kept current for the day
+                    # the block falls back to two launches (conv3 restored to fp32 weights)
+                    dop = item[1].dop
+                    self.launch_item(("conv", dop), st, L.OUT_F32, f32.data_ptr())
+                    L.check(lib.slq_absmax_scale(f32.data_ptr(), dop.M * dop.Cout, sc, dop.out_id, 127, tmp, st))
+                    settle(dop.out_id)
+                self.launch_item(item, st, L.OUT_F32, f32.data_ptr())
+                L.check(lib.slq_absmax_scale(f32.data_ptr(), op.M * op.Cout, sc, op.out_id,
+                                             127 if op.signed else 255, tmp, st))
                 settle(op.out_id)
-                mode = L.OUT_S8 if op.signed else L.OUT_U8
-                e = self._epilogue(op, mode, self.act[op.out_id].data_ptr())
-                L.check(lib.slq_conv_launch(op.handle, ctypes.byref(e), st))
+                self.launch_item(item, st)
         self.calibrated = True
 
     def forward(self, x):
@@ -521,14 +611,12 @@ class Engine:
         lib = self.lib
         sc = self.act_scales.data_ptr()
         self._stem(x_ptr, self.act[0].data_ptr(), L.OUT_U8, st)
-        for op in self.ops:
-            mode = L.OUT_S8 if op.signed else L.OUT_U8
-            e = self._epilogue(op, mode, self.act[op.out_id].data_ptr())
-            L.check(lib.slq_conv_launch(op.handle, ctypes.byref(e), st))
+        for item in self.schedule:
+            self.launch_item(item, st)
         L.check(lib.slq_tail_forward(self.act[self.final_id].data_ptr(), self.N, self.final_hw, self.final_c,
                                      sc, self.final_id, self.fc_w_split.data_ptr(), self.fc_b.data_ptr(),
                                      self.logits.shape[1], self.tail_ws.data_ptr(), self.logits.data_ptr(), st))
-        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.ops) + 3
+        self.kernel_launches = (1 if self.stem is not None else 2) + len(self.schedule) + 3
 
     def _stem(self, x_ptr, out_ptr, mode, st):
         lib, sc = self.lib, self.act_scales.data_ptr()
@@ -579,6 +667,10 @@ class Engine:
                 for _desc, _wg, h, _pg in getattr(op, "variants", {}).values():
                     self.lib.slq_conv_destroy(h)
                 op.variants, op.handle = {}, None
+            for bt in getattr(self, "tails", []):
+                if bt.handle is not None:
+                    self.lib.slq_blocktail_destroy(bt.handle)
+                    bt.handle = None
             if getattr(self, "stem", None) is not None:
                 self.lib.slq_stem_destroy(self.stem)
                 self.stem = None

@@ -34,6 +34,16 @@ class Epilogue(ctypes.Structure):
                 ("in_rowsum", _vp), ("out_rowsum", _vp), ("in_planes", _i32), ("in_plane_stride", _i64)]
 
 
+class BlockTailDesc(ctypes.Structure):
+    _fields_ = [(n, _i32) for n in ("N", "H", "W", "Cin", "stride", "Cmid", "Cout", "impl")]
+
+
+class BlockTailEpilogue(ctypes.Structure):
+    _fields_ = [("wscale3", _vp), ("zf3", _vp), ("bias3", _vp), ("wscaled", _vp), ("zfd", _vp), ("biasd", _vp),
+                ("act_scales", _vp), ("in3_id", _i32), ("ind_id", _i32), ("out_id", _i32),
+                ("out", _vp), ("out_mode", _i32), ("out_rowsum", _vp)]
+
+
 # name -> (restype, argtypes); mirrors include/slq.h one to one (tests check the export list)
 SIGNATURES = {
     "slq_last_error": (ctypes.c_char_p, []),
@@ -57,6 +67,10 @@ SIGNATURES = {
     "slq_build_packed_gemm_weights": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "slq_conv_set_packed_weights": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "slq_conv_launch": (ctypes.c_int, [_vp, ctypes.POINTER(Epilogue), _vp]),
+    "slq_blocktail_create": (ctypes.c_int, [ctypes.POINTER(BlockTailDesc), _vp, _vp, _vp, _vp, ctypes.POINTER(_vp)]),
+    "slq_blocktail_destroy": (None, [_vp]),
+    "slq_blocktail_rowsum_planes": (_i32, [_vp]),
+    "slq_blocktail_launch": (ctypes.c_int, [_vp, ctypes.POINTER(BlockTailEpilogue), _vp]),
     "slq_debug_set_trace": (ctypes.c_int, [_vp, _i32]),
     "slq_stem_forward": (ctypes.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "slq_conv_rowsum_planes": (_i32, [_vp, _i32]),

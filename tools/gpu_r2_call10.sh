@@ -1,0 +1,22 @@
+#!/bin/bash
+# round 2, GPU call 10: fused block tail (conv3 + downsample conv in one launch)
+set +e
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_block_tail_gpu.py -x -q > gpurun_out/t_tail.log 2>&1; echo "block tail rc=$?"
+tail -n 40 gpurun_out/t_tail.log | cut -c1-400
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --layers gpurun_out/layers.txt > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"
+grep -v "mbarrier timeout" gpurun_out/bench.err | tail -c 1500
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['achieved'], d['roofline']['frac'], d['roofline']['conv_ms_per_step_serialised'], d['logits_rel_l2_vs_fp32'], d['top1_agreement_vs_fp32'], d['gpu_launches'])
+PY
+cat gpurun_out/layers.txt
+timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-agree --no-fuse-tail --layers gpurun_out/layers_nofuse.txt > gpurun_out/bench_nofuse.log 2> gpurun_out/bench_nofuse.err; echo "bench nofuse rc=$?"
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_nofuse.log').read().strip().splitlines()[-1])
+print("no fuse:", {k:d[k] for k in ('value','ms_per_step')}, d['roofline']['conv_ms_per_step_serialised'])
+PY
+timeout 2400 python -m pytest tests -m gpu -q --deselect tests/test_block_tail_gpu.py > gpurun_out/t_gpu.log 2>&1; echo "rest rc=$?"
+tail -n 8 gpurun_out/t_gpu.log | cut -c1-300
