@@ -15,9 +15,13 @@
 // and ONE epilogue folds them:  y = A3 (acc3 + z3 S3) + Ad ((lo + 256 hi) + zd Sd) + B ; ReLU ; u8.  The identity
 // never exists in HBM (and is never rounded to 8 bits).
 //
-// Two independent pipelines per CTA (tile i -> pipeline i & 1): producer warp -> MMA warp -> epilogue team of 8
-// warps, each with its own operand ring and TMEM accumulator; the CTA keeps the weights of ONE 64-channel n-tile
-// (both convs) resident in shared memory for its whole life.  sm_100a only.
+// Roles (640 threads, 1 CTA/SM): two operand pipelines (tile i -> pipeline i & 1: a TMA producer warp, an MMA warp, an
+// operand ring and a TMEM accumulator each) feed ONE epilogue crew of 16 warps that drains every tile together
+// (warp = TMEM lane quarter x 16-channel slice): the accumulator of tile i is free again after ~1/2 of the time an
+// 8-warp team needs, and while the crew works on tile i the other pipeline's MMAs for tile i + 1 run -- with one
+// accumulator per pipeline (2 x 224 of the 512 TMEM columns) the epilogue and the MMAs of the SAME pipeline can never
+// overlap, so a team per pipeline (the first version) paid MMA + epilogue per tile.  The CTA keeps the weights of ONE
+// 64-channel n-tile (both convs) resident in shared memory for its whole life.  sm_100a only.
 #include <algorithm>
 #include <new>
 
@@ -36,7 +40,8 @@ struct slq_blocktail {
 namespace slq {
 
 constexpr int kBtThreads = 640;
-constexpr int kBtTeam = 256;
+constexpr int kBtCrew = 512;      // epilogue threads
+constexpr int kBtStage = 3;       // output staging tiles (TMA store of tile i in flight while i + 1, i + 2 are staged)
 constexpr int kBtN3 = 80;    // UMMA N of the conv3 part: 64 channels + the ones group
 constexpr int kBtNd = 144;   // UMMA N of the downsample part: 64 low + 64 high limbs + the ones group
 constexpr int kBtAccCols = 256;  // TMEM columns per pipeline (224 used)
@@ -110,7 +115,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
     for (int p = 0; p < 2; ++p) {
       for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(p, s), 1); mbar_init(empty_bar(p, s), 1); }
       mbar_init(tfull_bar(p), 1);
-      mbar_init(tempty_bar(p), kBtTeam);
+      mbar_init(tempty_bar(p), kBtCrew);
     }
     mbar_init(bfull_bar, 1);
     fence_barrier_init();
@@ -207,18 +212,16 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ================================ epilogue teams ===========================================
+    // ================================ epilogue crew ============================================
     grid_dependency_wait();
-    const int p = (warp - 4) >> 3;
-    const int half = ((warp - 4) >> 2) & 1;   // channels [32 half, 32 half + 32) of the tile
-    const int wq = warp & 3;
-    const int et = threadIdx.x - 128 - p * kBtTeam;
+    const int slice = (warp - 4) >> 2;        // channels [16 slice, 16 slice + 16) of the tile
+    const int wq = warp & 3;                  // TMEM lane quarter this warp may read
+    const int et = threadIdx.x - 128;
     const int row = wq * 32 + lane;
     constexpr bool kQuant = OUT == SLQ_OUT_U8;
-    float *prm = reinterpret_cast<float *>(smem + a.prm_off) + p * 5 * 64;  // A3 | Z3 | Ad | Zd | B, 64 floats each
-    const uint32_t prm_s = smem_base + a.prm_off + p * 5 * 64 * 4;
-    volatile uint32_t *rs_scratch = reinterpret_cast<volatile uint32_t *>(smem + a.prm_off + 2 * 5 * 64 * 4) + p * 128;
-    const uint32_t stg = smem_base + a.out_off + p * (kTileM * 64);
+    float *prm = reinterpret_cast<float *>(smem + a.prm_off);  // A3 | Z3 | Ad | Zd | B, 64 floats each
+    const uint32_t prm_s = smem_base + a.prm_off + (uint32_t)slice * 64;
+    volatile uint32_t *rs_base = reinterpret_cast<volatile uint32_t *>(smem + a.prm_off + 5 * 64 * 4);  // [2][3][128]
     const uint32_t row_byte = (uint32_t)(row * 64), row_sw = (uint32_t)((row >> 1) & 3);
     if (et < 64) {  // the n-tile never changes: constants once
       const int oc = my_n * 64 + et;
@@ -227,74 +230,78 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
                                a.act_scales[a.in3_id], a.act_scales[a.ind_id], inv, kQuant);
       prm[et] = c.a3; prm[64 + et] = c.z3; prm[128 + et] = c.ad; prm[192 + et] = c.zd; prm[256 + et] = c.b;
     }
-    named_bar_sync(1 + p, kBtTeam);
-    const uint32_t tcol = tmem_base + ((uint32_t)(wq * 32) << 16) + p * kBtAccCols;
-    int t = 0;
-    for (int i = p; i < count; i += 2, ++t) {
+    named_bar_sync(1, kBtCrew);
+    const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const int c0 = slice * 16;
+    const bool want_rs = kQuant && a.out_rowsum != nullptr;
+    for (int i = 0; i < count; ++i) {
+      const int p = i & 1, t = i >> 1;          // pipeline / accumulator, and its tile ordinal
       const int m_tile = first_m + i * per_n;
       const long long m = (long long)m_tile * kTileM + row;
       const bool valid = m < a.M;
-      if (kQuant && et == 0) tma_store_wait_read();  // the staging tile is free again
-      named_bar_sync(1 + p, kBtTeam);
+      const uint32_t tcol = tlane + p * kBtAccCols;
       mbar_wait(tfull_bar(p), (uint32_t)(t & 1));
       tc_fence_after();
+      uint32_t a3[16], lo[16], hi[16];
+      tmem_ld16(tcol + c0, a3);
+      tmem_ld16(tcol + kBtN3 + c0, lo);
+      tmem_ld16(tcol + kBtN3 + 64 + c0, hi);
       const float S3 = (float)(int)tmem_ld1(tcol + 64);
       const float Sd = (float)(int)tmem_ld1(tcol + kBtN3 + 128);
       tmem_ld_wait();
-      uint32_t rsum = 0;
-#pragma unroll 1
-      for (int sub = 0; sub < 2; ++sub) {
-        const int c0 = half * 32 + sub * 16;
-        uint32_t a3[16], lo[16], hi[16];
-        tmem_ld16(tcol + c0, a3);
-        tmem_ld16(tcol + kBtN3 + c0, lo);
-        tmem_ld16(tcol + kBtN3 + 64 + c0, hi);
-        tmem_ld_wait();
-        uint32_t pk[4];
-        float *of = reinterpret_cast<float *>(a.out) + m * a.Cout + my_n * 64 + c0;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const uint32_t pofs = prm_s + (uint32_t)(c0 + 4 * q4) * 4;
-          const uint4 pa3 = lds128(pofs), pz3 = lds128(pofs + 256), pad = lds128(pofs + 512), pzd = lds128(pofs + 768),
-                      pb = lds128(pofs + 1024);
-          const uint32_t va3[4] = {pa3.x, pa3.y, pa3.z, pa3.w}, vz3[4] = {pz3.x, pz3.y, pz3.z, pz3.w};
-          const uint32_t vad[4] = {pad.x, pad.y, pad.z, pad.w}, vzd[4] = {pzd.x, pzd.y, pzd.z, pzd.w};
-          const uint32_t vb[4] = {pb.x, pb.y, pb.z, pb.w};
-          float v[4];
-#pragma unroll
-          for (int b = 0; b < 4; b += 2) {
-            const int j = 4 * q4 + b;
-            const float2 f3 = make_float2((float)(int)a3[j], (float)(int)a3[j + 1]);
-            const float2 fd = ffma2(make_float2((float)(int)hi[j], (float)(int)hi[j + 1]), make_float2(256.0f, 256.0f),
-                                    make_float2((float)(int)lo[j], (float)(int)lo[j + 1]));
-            float2 y = ffma2(make_float2(S3, S3), make_float2(__uint_as_float(vz3[b]), __uint_as_float(vz3[b + 1])),
-                             make_float2(__uint_as_float(vb[b]), __uint_as_float(vb[b + 1])));
-            y = ffma2(make_float2(Sd, Sd), make_float2(__uint_as_float(vzd[b]), __uint_as_float(vzd[b + 1])), y);
-            y = ffma2(f3, make_float2(__uint_as_float(va3[b]), __uint_as_float(va3[b + 1])), y);
-            y = ffma2(fd, make_float2(__uint_as_float(vad[b]), __uint_as_float(vad[b + 1])), y);
-            v[b] = y.x; v[b + 1] = y.y;
-          }
-          if (!kQuant) {
-            if (valid) reinterpret_cast<float4 *>(of)[q4] = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
-          } else {
-            pk[q4] = epi_pack4<false>(v[0], v[1], v[2], v[3]);  // saturation at 0 is the ReLU
-            rsum = __dp4a(pk[q4], 0x01010101u, rsum);
-          }
-        }
-        if (kQuant) sts128(stg + row_byte + ((((uint32_t)(c0 >> 4)) ^ row_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
-      }
-      const bool want_rs = kQuant && a.out_rowsum != nullptr;
-      if (want_rs && half == 1) rs_scratch[row] = rsum;
       tc_fence_before();
-      mbar_arrive(tempty_bar(p));
+      mbar_arrive(tempty_bar(p));  // everything of this tile is in registers: the pipeline's next MMAs may start
+      uint32_t pk[4];
+      float *of = reinterpret_cast<float *>(a.out) + m * a.Cout + my_n * 64 + c0;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t pofs = prm_s + (uint32_t)q4 * 16;
+        const uint4 pa3 = lds128(pofs), pz3 = lds128(pofs + 256), pad = lds128(pofs + 512), pzd = lds128(pofs + 768),
+                    pb = lds128(pofs + 1024);
+        const uint32_t va3[4] = {pa3.x, pa3.y, pa3.z, pa3.w}, vz3[4] = {pz3.x, pz3.y, pz3.z, pz3.w};
+        const uint32_t vad[4] = {pad.x, pad.y, pad.z, pad.w}, vzd[4] = {pzd.x, pzd.y, pzd.z, pzd.w};
+        const uint32_t vb[4] = {pb.x, pb.y, pb.z, pb.w};
+        float v[4];
+#pragma unroll
+        for (int b = 0; b < 4; b += 2) {
+          const int j = 4 * q4 + b;
+          const float2 f3 = make_float2((float)(int)a3[j], (float)(int)a3[j + 1]);
+          const float2 fd = ffma2(make_float2((float)(int)hi[j], (float)(int)hi[j + 1]), make_float2(256.0f, 256.0f),
+                                  make_float2((float)(int)lo[j], (float)(int)lo[j + 1]));
+          float2 y = ffma2(make_float2(S3, S3), make_float2(__uint_as_float(vz3[b]), __uint_as_float(vz3[b + 1])),
+                           make_float2(__uint_as_float(vb[b]), __uint_as_float(vb[b + 1])));
+          y = ffma2(make_float2(Sd, Sd), make_float2(__uint_as_float(vzd[b]), __uint_as_float(vzd[b + 1])), y);
+          y = ffma2(f3, make_float2(__uint_as_float(va3[b]), __uint_as_float(va3[b + 1])), y);
+          y = ffma2(fd, make_float2(__uint_as_float(vad[b]), __uint_as_float(vad[b + 1])), y);
+          v[b] = y.x; v[b + 1] = y.y;
+        }
+        if (!kQuant) {
+          if (valid) reinterpret_cast<float4 *>(of)[q4] = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
+        } else {
+          pk[q4] = epi_pack4<false>(v[0], v[1], v[2], v[3]);  // saturation at 0 is the ReLU
+        }
+      }
       if (kQuant) {
+        const uint32_t stg = smem_base + a.out_off + (uint32_t)(i % kBtStage) * (kTileM * 64);
+        sts128(stg + row_byte + (((uint32_t)slice ^ row_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        uint32_t rsum = 0;
+        volatile uint32_t *rs_scratch = rs_base + (i & 1) * 384;  // tile i + 1 must not overwrite what tile i still reads
+        if (want_rs) {
+          rsum = __dp4a(pk[0], 0x01010101u, __dp4a(pk[1], 0x01010101u, __dp4a(pk[2], 0x01010101u, __dp4a(pk[3], 0x01010101u, 0u))));
+          if (slice != 0) rs_scratch[(slice - 1) * 128 + row] = rsum;
+        }
         fence_proxy_async_smem();
-        named_bar_sync(1 + p, kBtTeam);
+        named_bar_sync(1, kBtCrew);
         if (et == 0) {
           tma_store_2d(&tmO, stg, my_n * 64, m_tile * kTileM);
           tma_store_commit();
+          // at most the two newest stores still read their staging tiles: the tile that tile i + 1 overwrites
+          // (i + 1 - kBtStage = i - 2) is free before this thread reaches the next barrier
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        if (want_rs && half == 0 && valid) a.out_rowsum[(long long)my_n * a.M + m] = rsum + rs_scratch[row];
+        if (want_rs && slice == 0) {
+          if (valid) a.out_rowsum[(long long)my_n * a.M + m] = rsum + rs_scratch[row] + rs_scratch[128 + row] + rs_scratch[256 + row];
+        }
       }
     }
     if (kQuant && et == 0) tma_store_wait_all();
@@ -420,13 +427,13 @@ static int bt_launch(slq_blocktail *h, const BtArgs &a, cudaStream_t st) {
 
 using namespace slq;
 
-// shared-memory plan: resident weights of one n-tile (both convs) + two operand rings + two staging tiles +
+// shared-memory plan: resident weights of one n-tile (both convs) + two operand rings + three staging tiles +
 // constants + barriers.  Returns the bytes to request, or -1 if it does not fit (the caller then keeps the two
 // separate launches).
 static int bt_plan(const slq_blocktail_desc *d, int swz, int *stages, int off[6]) {
   const int k3 = d->Cmid / swz, kd = d->Cin / swz;
   const int b3 = k3 * kBtN3 * swz, bd = kd * kBtNd * swz;
-  const int fixed = b3 + bd + 2 * kTileM * 64 + (2 * 5 * 64 * 4 + 2 * 128 * 4) + 512 + 1024;
+  const int fixed = b3 + bd + kBtStage * kTileM * 64 + (5 * 64 * 4 + 2 * 3 * 128 * 4) + 512 + 1024;
   const int a_bytes = kTileM * swz;
   int st = std::min(kBtMaxStages, (232448 - fixed) / (2 * a_bytes));
   if (st < 2) return -1;
@@ -435,8 +442,8 @@ static int bt_plan(const slq_blocktail_desc *d, int swz, int *stages, int off[6]
   off[1] = b3;                       // bd
   off[2] = b3 + bd;                  // ring (both pipelines)
   off[3] = off[2] + 2 * st * a_bytes;  // output staging
-  off[4] = off[3] + 2 * kTileM * 64;   // constants + row-sum scratch
-  off[5] = off[4] + 2 * 5 * 64 * 4 + 2 * 128 * 4;  // barriers
+  off[4] = off[3] + kBtStage * kTileM * 64;   // constants + row-sum scratch
+  off[5] = off[4] + 5 * 64 * 4 + 2 * 3 * 128 * 4;  // barriers
   return 1024 + off[5] + 512;
 }
 

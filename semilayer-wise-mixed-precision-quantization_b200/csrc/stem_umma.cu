@@ -563,14 +563,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     // ONE tensor load per pair: box {W, 2 rows, 3 channels} of the image viewed as [3N planes][H][W]; rows
     // above / below the image are zero-filled by the TMA unit (the conv's padding).  (Six 1-D bulk copies
     // per pair cost the issuing thread ~1800 cycles -- more than everything else in the kernel.)
-    int g = 0;
+    int g = 0, tn = 0;
     const uint32_t pair_bytes = (uint32_t)(6 * row_bytes);
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
       for (int t = p0 - 2; t <= p1; ++t, ++g) {
         const int s = g & (kTsSlots - 1);
+        if (lane == 0) stem_trace(a, 0, tn, 0, g);
         mbar_wait(sempty_bar(s), (uint32_t)(((g >> 3) & 1) ^ 1));
+        if (lane == 0) stem_trace(a, 0, tn, 1, g);
         if (elect_one()) {
           mbar_expect_tx(sfull_bar(s), pair_bytes);
           tma_load_3d(smem_base + kTsStageOff + s * kTsStageBytes, &tmX, sfull_bar(s), 0, 2 * t, 3 * n);
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     const int q = quarter * 32 + lane;               // output column == TMEM lane
     __half *rowbuf = reinterpret_cast<__half *>(smem + kTsRowBufOff);
     const int w4 = a.W >> 2;                         // 4-element groups per row (<= 64)
-    int g = 0;
+    int g = 0, tn = 0;
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
@@ -594,7 +596,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         const int s = g & (kTsSlots - 1);
         const uint32_t ph = (uint32_t)((g >> 3) & 1);
         __half *rb = rowbuf + (g & 1) * 6 * kTsRowP;
+        if (bt == 0) stem_trace(a, 1, tn, 2, g);
         mbar_wait(sfull_bar(s), ph);
+        if (bt == 0) stem_trace(a, 1, tn, 3, g);
         // 1. raw -> fp16, every element once: thread = (row r6 of the six, 4-element group c4); two passes
         const uint8_t *stg = smem + kTsStageOff + s * kTsStageBytes;
 #pragma unroll
@@ -626,7 +630,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         named_bar_sync(1, kTsBuilders);  // rows complete; also: nobody still reads the buffer of pair g - 2
         if (lane == 0) mbar_arrive(sempty_bar(s));  // the staging slot may be refilled
         // 2. the pair's TMEM slot must be free: the four conv rows that used pair g - 8 have completed
+        if (bt == 0) stem_trace(a, 1, tn, 4, g);
         if (g >= kTsSlots) mbar_wait(pfree_bar(s), ph ^ 1);
+        if (bt == 0) stem_trace(a, 1, tn, 5, g);
         tc_fence_after();
         // 3. this thread's 16-byte windows x[c][h][2q-3 .. 2q+4] -> the slab's TMEM columns
         const uint32_t tslab = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTsSlabBase + s * kTsSlotCols;
@@ -640,6 +646,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(pfull_bar(s));
+        if (bt == 0) stem_trace(a, 1, tn, 6, g);
       }
     }
   } else if (warp <= kTsBuildW + kTsMmaW) {
@@ -648,7 +655,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t db0 = make_smem_desc<128>(smem_base + kTsBOff);
-    int rc = 0, u_ord = 0;
+    int rc = 0, u_ord = 0, tn = 0;
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x, ++u_ord) {
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
@@ -656,10 +663,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         if ((rc & 3) != mw) continue;
         const int acc = rc & 3;
         const int g_lo = rc + 3 * u_ord;
+        if (lane == 0) stem_trace(a, 2 + mw, tn, 7, rc);
         if (rc >= 4) mbar_wait(tempty_bar(acc), (uint32_t)(((rc >> 2) & 1) ^ 1));
+        if (lane == 0) stem_trace(a, 2 + mw, tn, 8, rc);
         // pairs complete in order: the newest one implies the three before it
         mbar_wait(pfull_bar((g_lo + 3) & (kTsSlots - 1)), (uint32_t)(((g_lo + 3) >> 3) & 1));
         tc_fence_after();
+        if (lane == 0) stem_trace(a, 2 + mw, tn, 9, rc);
         if (elect_one()) {
 #pragma unroll
           for (int i = 0; i < 4 && !(SF_DBG(a) & 8); ++i) {
@@ -684,6 +694,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
           umma_commit(tfull_bar(acc));
         }
         __syncwarp();
+        if (lane == 0) stem_trace(a, 2 + mw, tn, 10, rc);
       }
     }
   } else if (warp <= kTsBuildW + kTsMmaW + kTsEpiW) {
@@ -695,13 +706,15 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     uint8_t *cring = smem + kTsConvOff;
     const bool f32_out = a.out_mode == SLQ_OUT_F32;
     uint32_t vm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // running vertical maximum of the pooling window (packed u8)
-    int rc = 0, ve = 0;                          // conv rows / pooled rows handled so far by this CTA
+    int rc = 0, ve = 0, tn = 0;                  // conv rows / pooled rows handled so far by this CTA
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
       for (int p = p0; p < p1; ++p, ++rc) {
         const int acc = rc & 3;
+        if (et == 0) stem_trace(a, 6, tn, 11, rc);
         mbar_wait(tfull_bar(acc), (uint32_t)((rc >> 2) & 1));
+        if (et == 0) stem_trace(a, 6, tn, 12, rc);
         tc_fence_after();
         uint32_t av[32];
         tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kTsAccCols + half * 32, av);
@@ -709,6 +722,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: row rc + 4 may start
+        if (et == 0) stem_trace(a, 6, tn, 13, rc);
         if (SF_DBG(a) & 4) continue;
         float y[32];
 #pragma unroll
@@ -750,7 +764,9 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         if (emit) {
           // hand the vertically pooled row to the pool warps through a 4-slot ring
           const int vs = ve & 3;
+          if (et == 0) stem_trace(a, 6, tn, 14, rc);
           if (ve >= 4) mbar_wait(vfree_bar(vs), (uint32_t)(((ve >> 2) & 1) ^ 1));
+          if (et == 0) stem_trace(a, 6, tn, 15, rc);
           uint4 *dst = reinterpret_cast<uint4 *>(cring + vs * kSfConvRowBytes + q * 64 + half * 32);
           dst[0] = make_uint4(vm[0], vm[1], vm[2], vm[3]);
           dst[1] = make_uint4(vm[4], vm[5], vm[6], vm[7]);
@@ -770,14 +786,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     // for a pooled row to be written out)
     const int pt = threadIdx.x - (1 + kTsBuildW + kTsMmaW + kTsEpiW) * 32;  // 0..127
     const uint8_t *cring = smem + kTsConvOff;
-    int ve = 0;
+    int ve = 0, tn = 0;
     if (a.out_mode != SLQ_OUT_F32 && !(SF_DBG(a) & 4)) {  // (debug bit 4: the epilogue emits nothing)
       for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
         int n, j0, j1, p0, p1;
         unit_rows(a, u, n, j0, j1, p0, p1);
         for (int jrow = j0; jrow < j1; ++jrow, ++ve) {
           const int vs = ve & 3;
+          if (pt == 0) stem_trace(a, 7, tn, 16, ve);
           mbar_wait(vfull_bar(vs), (uint32_t)((ve >> 2) & 1));
+          if (pt == 0) stem_trace(a, 7, tn, 17, ve);
           const uint8_t *vrow = cring + vs * kSfConvRowBytes;
           uint4 *orow = reinterpret_cast<uint4 *>(reinterpret_cast<uint8_t *>(a.out) +
                                                   (((long long)n * a.Hp + jrow) * a.Wp) * 64);
@@ -803,6 +821,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(vfree_bar(vs));
+          if (pt == 0) stem_trace(a, 7, tn, 18, ve);
         }
       }
     }

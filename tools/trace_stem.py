@@ -18,7 +18,7 @@ L.check(lib.slq_stem_create(N, H, W, ws.data_ptr(), ctypes.byref(h)))
 L.check(lib.slq_stem_set_weights(h, w.data_ptr(), L.current_stream()))
 out = torch.empty(N * 56 * 56 * 64, dtype=torch.uint8, device="cuda")
 scratch = torch.empty(16, device="cuda")
-cap = 24 * 800
+cap = 24 * 2400
 buf = torch.zeros(3 * cap, dtype=torch.int64, device="cuda")
 for rep in range(2):
     buf.zero_(); torch.cuda.synchronize()
@@ -32,13 +32,26 @@ keep = hh[:, 0] > 0
 ev = np.concatenate([hh[keep], issuer[keep, None]], 1)
 ev[:, 0] -= 1
 ev = ev[np.argsort(ev[:, 2], kind="stable")]
-names = {0: "BLD row start", 1: "BLD aempty ok", 2: "BLD built", 3: "BLD arrived", 8: "BLD row end", 4: "MMA go", 9: "MMA issued",
-         5: "EPI tfull ok", 10: "EPI stored", 11: "EPI bar ok", 6: "EPI row end"}
+if os.environ.get("STEM_OLD"):
+    names = {0: "BLD row start", 1: "BLD aempty ok", 2: "BLD built", 3: "BLD arrived", 8: "BLD row end", 4: "MMA go", 9: "MMA issued",
+             5: "EPI tfull ok", 10: "EPI stored", 11: "EPI bar ok", 6: "EPI row end"}
+else:  # stem_ts_kernel: issuer 0 producer, 1 builder thread 0, 2-5 MMA warps, 6 epilogue thread 0, 7 pool thread 0
+    names = {0: "PRD top", 1: "PRD sempty ok", 2: "BLD top", 3: "BLD sfull ok", 4: "BLD converted", 5: "BLD pfree ok",
+             6: "BLD stored", 7: "MMA top", 8: "MMA tempty ok", 9: "MMA pfull ok", 10: "MMA issued", 11: "EPI top",
+             12: "EPI tfull ok", 13: "EPI loaded", 14: "EPI emit", 15: "EPI vfree ok", 16: "POOL top", 17: "POOL vfull ok",
+             18: "POOL done"}
 t0 = ev[0, 2]
-lo, hi = int(os.environ.get("TRACE_FROM", "300")), int(os.environ.get("TRACE_TO", "420"))
+lo, hi = int(os.environ.get("TRACE_FROM", "600")), int(os.environ.get("TRACE_TO", "760"))
 for e, idx, t, who in ev[lo:hi]:
-    print("%8d  %-14s row %4d (issuer %d)" % (t - t0, names.get(int(e), str(e)), idx, who))
-for e in (0, 4, 5):
-    tt = ev[ev[:, 0] == e][:, 2]
-    if len(tt) > 10:
-        print(names[e], "period median %.0f clk" % np.median(np.diff(tt)))
+    print("%8d  %-14s idx %4d (issuer %d)" % (t - t0, names.get(int(e), str(e)), idx, who))
+# per role: where the time of one loop trip goes (mean clocks from each event to the next one of the same issuer)
+for who in sorted(set(ev[:, 3].tolist())):
+    sub = ev[ev[:, 3] == who]
+    sub = sub[len(sub) // 4:]          # steady state
+    if len(sub) < 20:
+        continue
+    d = np.diff(sub[:, 2])
+    print("issuer %d: %d events, span %d clk" % (who, len(sub), sub[-1, 2] - sub[0, 2]))
+    for e in sorted(set(sub[:-1, 0].tolist())):
+        m = sub[:-1, 0] == e
+        print("    after %-14s mean %7.0f clk  (n=%d, total %d)" % (names.get(int(e), str(e)), d[m].mean(), m.sum(), d[m].sum()))
