@@ -67,14 +67,15 @@ struct SmemPlan {
   int mma_warps;     // 2: warps 1 and 3 issue MMAs (1: warp 1 only; experiments)
   int b_off;
   int res_bufs;      // depth of the residual (block identity) prefetch ring, 0 without residual
-  int out_bufs;      // output staging tiles: one per epilogue team, ONE shared by both (streamed weights), or
-                     // NONE (256-channel tiles store straight from registers)
+  int out_bufs;      // output staging tiles: TWO per epilogue team (resident weights, when they fit: the TMA store of a
+                     // tile is still reading one while the team fills the other -- one team barrier per tile), one
+                     // per team, ONE shared by both (streamed weights), or NONE (256-channel tiles store from registers)
   int out_off, res_off, prm_off, bar_off;
   int total;         // dynamic smem bytes to request (including 1024 B of alignment slack)
 };
 
 constexpr int kMaxResBufs = 4;
-constexpr int kPrmBytes = 2 * 3 * 256 * 4 + 2 * 128 * 4;  // per team: A[256] | Z[256] | B[256] floats; then 128 u32 of row-sum scratch per team
+constexpr int kPrmBytes = 2 * 3 * 256 * 4 + 4 * 128 * 4;  // per team: A[256] | Z[256] | B[256] floats; then 2 x 128 u32 of row-sum scratch per team
 constexpr int kMaxGroup = 4;
 
 inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
@@ -102,6 +103,8 @@ inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
       const int st = (int)std::min<long long>(kMaxStages, room / ((long long)grp * p.a_bytes)) & ~1;
       if (st >= (grp == 1 ? 4 : 4)) {
         p.b_resident = 1; p.group = grp; p.stages = st; p.stage_bytes = grp * p.a_bytes; p.res_bufs = rb; p.out_bufs = 2;
+        const int st4 = (int)std::min<long long>(kMaxStages, (room - 2 * kOutTileBytes) / ((long long)grp * p.a_bytes)) & ~1;
+        if (st4 >= 4) { p.out_bufs = 4; p.stages = st4; }
         break;
       }
     }
@@ -572,10 +575,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // data pipe was the busiest unit of the epilogue with one {A,Z,B,pad} load per output), so one load
     // fetches the same constant of FOUR channels: 3 wavefronts per channel instead of 4, 0.75 loads per output.
     float *prm = reinterpret_cast<float *>(smem + sp.prm_off) + team * 768;
-    volatile uint32_t *rs_scratch = reinterpret_cast<volatile uint32_t *>(smem + sp.prm_off + 2 * 3072) + team * 128;
+    volatile uint32_t *rs_base = reinterpret_cast<volatile uint32_t *>(smem + sp.prm_off + 2 * 3072) + team * 256;
     const uint32_t prm_s = smem_base + sp.prm_off + team * 3072;
     const bool shared_stg = sp.out_bufs == 1;  // both teams stage through one tile (stfree hand-off below)
-    const uint32_t stg = smem_base + sp.out_off + (shared_stg ? 0 : team) * kOutTileBytes;
+    const bool dbl_stg = sp.out_bufs == 4;     // two tiles per team, alternating: no wait for the store at the loop top
+    const uint32_t stg_base = smem_base + sp.out_off + (shared_stg ? 0 : team * (dbl_stg ? 2 : 1)) * kOutTileBytes;
     float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
     if (OUT != SLQ_OUT_ACC) {
       s_in = e.act_scales[e.in_id];
@@ -704,9 +708,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       walk.at(it, m_tile, n_tile);
       const int acc = it % a.acc_bufs, tb = it % kTileBars;
       const uint32_t ph = (uint32_t)((it / kTileBars) & 1);
-      // staging tile free again? (the previous TMA store of this team has read it)
-      if (!kWide && a.tma_out && et == 0) tma_store_wait_read();
-      named_bar_sync(1 + team, kTeam);
+      const uint32_t stg = stg_base + (dbl_stg ? (uint32_t)((it >> 1) & 1) * kOutTileBytes : 0u);
+      volatile uint32_t *rs_scratch = rs_base + ((it >> 1) & 1) * 128;
+      if (!dbl_stg || (n_tile != last_n_tile && OUT != SLQ_OUT_ACC)) {
+        // staging tile free again? (the previous TMA store of this team has read it)  With two staging tiles per
+        // team nothing is waited for here; the barrier is then only needed before the constants are rewritten
+        if (!kWide && a.tma_out && et == 0 && !dbl_stg) tma_store_wait_read();
+        named_bar_sync(1 + team, kTeam);
+      }
       if (n_tile != last_n_tile && OUT != SLQ_OUT_ACC) {
         if (et < g.bn_ch) {
           const int oc = n_tile * g.bn_ch + et;
@@ -833,6 +842,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (want_rs) named_bar_sync(1 + team, kTeam);  // the scratch row sums are visible
       } else {
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        // two staging tiles: the store issued one tile ago (it read the OTHER tile, which the team fills next) has
+        // long finished reading; making sure of it before the barrier costs nothing and keeps the hand-off exact
+        if (dbl_stg && et == 0) tma_store_wait_read();
         named_bar_sync(1 + team, kTeam);
         if (et == 0) {
           tma_store_2d(&tmO, stg, n_tile * g.bn_ch, (int)(m_tile * kTileM));  // rows >= M are clipped

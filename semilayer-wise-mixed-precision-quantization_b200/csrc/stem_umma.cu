@@ -452,8 +452,8 @@ constexpr int kTsConvOff = kTsBOff + kSfBBytes;
 constexpr int kTsPrmOff = kTsConvOff + kSfConvRing * kSfConvRowBytes;
 constexpr int kTsBarOff = kTsPrmOff + 64 * 8;
 constexpr int kTsSmemBytes = 1024 + kTsBarOff + 512;
-constexpr int kTsBuildW = 8, kTsMmaW = 4, kTsEpiW = 8, kTsPoolW = 4;
-constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW + kTsPoolW;  // producer + builders + MMA + epilogue + pool = 25
+constexpr int kTsBuildW = 8, kTsMmaW = 2, kTsEpiW = 16, kTsPoolW = 2;
+constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW + kTsPoolW;  // producer + builders + MMA + epilogue + pool = 29
 constexpr int kTsThreads = kTsWarps * 32;
 constexpr int kTsBuilders = kTsBuildW * 32, kTsEpi = kTsEpiW * 32;
 constexpr int kTsAccCols = 64, kTsSlabBase = 256, kTsSlotCols = 24;
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     }
   } else if (warp <= kTsBuildW + kTsMmaW) {
     // ================================ MMA issuers (convergent warps, elected lane) =============
-    const int mw = warp - (kTsBuildW + 1);  // conv rows with rc % 4 == mw
+    const int mw = warp - (kTsBuildW + 1);  // conv rows with rc % kTsMmaW == mw
     const uint32_t idesc = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint64_t db0 = make_smem_desc<128>(smem_base + kTsBOff);
@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
       for (int p = p0; p < p1; ++p, ++rc) {
-        if ((rc & 3) != mw) continue;
+        if ((rc & (kTsMmaW - 1)) != mw) continue;
         const int acc = rc & 3;
         const int g_lo = rc + 3 * u_ord;
         if (lane == 0) stem_trace(a, 2 + mw, tn, 7, rc);
@@ -699,13 +699,16 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     }
   } else if (warp <= kTsBuildW + kTsMmaW + kTsEpiW) {
     // ================================ epilogue: accumulator -> u8, vertical half of the pooling ====
-    const int et = threadIdx.x - (1 + kTsBuildW + kTsMmaW) * 32;  // 0..255
-    const int wq = warp & 3, half = (warp - (1 + kTsBuildW + kTsMmaW)) >> 2;  // TMEM lane quarter, channel half
+    const int et = threadIdx.x - (1 + kTsBuildW + kTsMmaW) * 32;  // 0..511
+    // TMEM lane quarter, and which 16 of the 64 channels: sixteen warps drain a conv row together, so the row's
+    // accumulator is free again (and the row is pooled) in half the time eight warps with 32 channels each needed --
+    // the per-row chain wait -> tcgen05.ld -> convert -> pack of these warps is what paced the whole kernel
+    const int wq = warp & 3, sl = (warp - (1 + kTsBuildW + kTsMmaW)) >> 2;
     const int q = wq * 32 + lane;
     const float2 *prm = reinterpret_cast<const float2 *>(smem + kTsPrmOff);
     uint8_t *cring = smem + kTsConvOff;
     const bool f32_out = a.out_mode == SLQ_OUT_F32;
-    uint32_t vm[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // running vertical maximum of the pooling window (packed u8)
+    uint32_t vm[4] = {0, 0, 0, 0};  // running vertical maximum of the pooling window (packed u8)
     int rc = 0, ve = 0, tn = 0;                  // conv rows / pooled rows handled so far by this CTA
     for (int u = blockIdx.x; u < a.total_units; u += gridDim.x) {
       int n, j0, j1, p0, p1;
@@ -716,18 +719,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         mbar_wait(tfull_bar(acc), (uint32_t)((rc >> 2) & 1));
         if (et == 0) stem_trace(a, 6, tn, 12, rc);
         tc_fence_after();
-        uint32_t av[32];
-        tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kTsAccCols + half * 32, av);
+        uint32_t av[16];
+        tmem_ld16(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * kTsAccCols + sl * 16, av);
         tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));  // accumulator is in registers: row rc + 4 may start
         if (et == 0) stem_trace(a, 6, tn, 13, rc);
         if (SF_DBG(a) & 4) continue;
-        float y[32];
+        float y[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const float4 p4 = *reinterpret_cast<const float4 *>(&prm[half * 32 + j]);  // {a0, b0, a1, b1}
+        for (int j = 0; j < 16; j += 2) {
+          const float4 p4 = *reinterpret_cast<const float4 *>(&prm[sl * 16 + j]);  // {a0, b0, a1, b1}
           const float2 r = ffma2(make_float2(__uint_as_float(av[j]), __uint_as_float(av[j + 1])),
                                  make_float2(p4.x, p4.z), make_float2(p4.y, p4.w));  // u8: in units of the output scale
           y[j] = r.x; y[j + 1] = r.y;
@@ -735,27 +738,27 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         if (f32_out) {
           if (q < a.Wc) {
             float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.out) +
-                                                   (((long long)n * a.Hc + p) * a.Wc + q) * 64 + half * 32);
+                                                   (((long long)n * a.Hc + p) * a.Wc + q) * 64 + sl * 16);
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < 4; ++j)
               o[j] = make_float4(fmaxf(y[4 * j], 0.f), fmaxf(y[4 * j + 1], 0.f), fmaxf(y[4 * j + 2], 0.f),
                                  fmaxf(y[4 * j + 3], 0.f));
           }
           continue;
         }
-        uint32_t pk[8];
+        uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)  // saturation at 0 is the ReLU
+        for (int j = 0; j < 4; ++j)  // saturation at 0 is the ReLU
           pk[j] = epi_pack4<false>(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         // 3x3 / stride-2 max-pool, separable: the VERTICAL maximum over conv rows 2j-1, 2j, 2j+1 is kept in
         // registers (this thread always owns the same column and channels), so only every second row goes to
         // shared memory and costs a barrier; the horizontal maximum then reads 3 pixels instead of 9
         if (p == p0) {  // the first conv row of a unit opens a window (and closes none)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) vm[j] = pk[j];
+          for (int j = 0; j < 4; ++j) vm[j] = pk[j];
         } else {        // rows 2j and 2j+1 extend the window that row 2j-1 opened
 #pragma unroll
-          for (int j = 0; j < 8; ++j) vm[j] = __vmaxu4(vm[j], pk[j]);
+          for (int j = 0; j < 4; ++j) vm[j] = __vmaxu4(vm[j], pk[j]);
         }
         const int jrow = p >> 1;
         // pooled row jrow is complete with an odd conv row (or the last one); the seam row 2 j0 - 1 at the start
@@ -767,16 +770,14 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
           if (et == 0) stem_trace(a, 6, tn, 14, rc);
           if (ve >= 4) mbar_wait(vfree_bar(vs), (uint32_t)(((ve >> 2) & 1) ^ 1));
           if (et == 0) stem_trace(a, 6, tn, 15, rc);
-          uint4 *dst = reinterpret_cast<uint4 *>(cring + vs * kSfConvRowBytes + q * 64 + half * 32);
-          dst[0] = make_uint4(vm[0], vm[1], vm[2], vm[3]);
-          dst[1] = make_uint4(vm[4], vm[5], vm[6], vm[7]);
+          *reinterpret_cast<uint4 *>(cring + vs * kSfConvRowBytes + q * 64 + sl * 16) = make_uint4(vm[0], vm[1], vm[2], vm[3]);
           __syncwarp();
           if (lane == 0) mbar_arrive(vfull_bar(vs));
           ++ve;
         }
         if (p & 1) {  // an odd row also opens the next window
 #pragma unroll
-          for (int j = 0; j < 8; ++j) vm[j] = pk[j];
+          for (int j = 0; j < 4; ++j) vm[j] = pk[j];
         }
       }
     }
