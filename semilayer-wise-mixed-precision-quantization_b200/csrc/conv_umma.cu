@@ -104,7 +104,7 @@ inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
       if (st >= (grp == 1 ? 4 : 4)) {
         p.b_resident = 1; p.group = grp; p.stages = st; p.stage_bytes = grp * p.a_bytes; p.res_bufs = rb; p.out_bufs = 2;
         const int st4 = (int)std::min<long long>(kMaxStages, (room - 2 * kOutTileBytes) / ((long long)grp * p.a_bytes)) & ~1;
-        if (st4 >= 4) { p.out_bufs = 4; p.stages = st4; }
+        if (st4 >= st) { p.out_bufs = 4; p.stages = st4; }  // only where the operand ring keeps its depth
         break;
       }
     }

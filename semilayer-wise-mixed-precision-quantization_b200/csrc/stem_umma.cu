@@ -452,8 +452,8 @@ constexpr int kTsConvOff = kTsBOff + kSfBBytes;
 constexpr int kTsPrmOff = kTsConvOff + kSfConvRing * kSfConvRowBytes;
 constexpr int kTsBarOff = kTsPrmOff + 64 * 8;
 constexpr int kTsSmemBytes = 1024 + kTsBarOff + 512;
-constexpr int kTsBuildW = 8, kTsMmaW = 2, kTsEpiW = 16, kTsPoolW = 2;
-constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW + kTsPoolW;  // producer + builders + MMA + epilogue + pool = 29
+constexpr int kTsBuildW = 8, kTsMmaW = 2, kTsEpiW = 16, kTsPoolW = 4;
+constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW + kTsPoolW;  // producer + builders + MMA + epilogue + pool = 31
 constexpr int kTsThreads = kTsWarps * 32;
 constexpr int kTsBuilders = kTsBuildW * 32, kTsEpi = kTsEpiW * 32;
 constexpr int kTsAccCols = 64, kTsSlabBase = 256, kTsSlotCols = 24;
