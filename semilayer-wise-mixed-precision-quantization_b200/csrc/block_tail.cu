@@ -22,6 +22,11 @@
 // accumulator per pipeline (2 x 224 of the 512 TMEM columns) the epilogue and the MMAs of the SAME pipeline can never
 // overlap, so a team per pipeline (the first version) paid MMA + epilogue per tile.  The CTA keeps the weights of ONE
 // 64-channel n-tile (both convs) resident in shared memory for its whole life.  sm_100a only.
+//
+// Measured and NOT kept: reading the accumulators in the 16x256b (mma fragment) shape, so that a thread always owns
+// the same four channels and their 20 constants stay in registers instead of 1.25 broadcast LDS.128 per output --
+// bit-identical results, but 166 / 97 / 82 us per launch against 140 / 93 / 76 us for this version (the byte-pair
+// shared-memory stores and the quad shuffles of the window sums cost more than the constant loads they replace).
 #include <algorithm>
 #include <new>
 
@@ -213,20 +218,16 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
     }
   } else if (warp >= 4) {
     // ================================ epilogue crew ============================================
-    // Accumulators are read in the 16x256b shape (the mma fragment layout): lane = 4 g + q holds, of a 16-row x
-    // 16-column block, rows g and g + 8 and the column pairs 2 q + {0, 1} and 8 + 2 q + {0, 1}.  A thread therefore
-    // always works on the SAME four channels of the CTA's n-tile: their 20 constants live in registers for the
-    // CTA's whole life.  (With the 32x32b shape -- lane = row, all 16 columns -- every output needed 1.25 warp-wide
-    // broadcast LDS.128 of constants, four LSU wavefronts each: 1280 wavefronts per tile, and the tile took 1620
-    // cycles.)
     grid_dependency_wait();
     const int slice = (warp - 4) >> 2;        // channels [16 slice, 16 slice + 16) of the tile
     const int wq = warp & 3;                  // TMEM lane quarter this warp may read
     const int et = threadIdx.x - 128;
-    const int g = lane >> 2, q = lane & 3;
+    const int row = wq * 32 + lane;
     constexpr bool kQuant = OUT == SLQ_OUT_U8;
     float *prm = reinterpret_cast<float *>(smem + a.prm_off);  // A3 | Z3 | Ad | Zd | B, 64 floats each
-    volatile uint32_t *rs_base = reinterpret_cast<volatile uint32_t *>(smem + a.prm_off + 5 * 64 * 4);  // [2][4][128]
+    const uint32_t prm_s = smem_base + a.prm_off + (uint32_t)slice * 64;
+    volatile uint32_t *rs_base = reinterpret_cast<volatile uint32_t *>(smem + a.prm_off + 5 * 64 * 4);  // [2][3][128]
+    const uint32_t row_byte = (uint32_t)(row * 64), row_sw = (uint32_t)((row >> 1) & 3);
     if (et < 64) {  // the n-tile never changes: constants once
       const int oc = my_n * 64 + et;
       const float inv = kQuant ? __fdiv_rn(1.0f, a.act_scales[a.out_id]) : 1.0f;
@@ -235,79 +236,65 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       prm[et] = c.a3; prm[64 + et] = c.z3; prm[128 + et] = c.ad; prm[192 + et] = c.zd; prm[256 + et] = c.b;
     }
     named_bar_sync(1, kBtCrew);
-    const int c0 = slice * 16;
-    // this thread's channels: c0 + 8 k + 2 q + e  (k, e in {0, 1});  constants as (e = 0, e = 1) pairs per k
-    float2 kA3[2], kZ3[2], kAd[2], kZd[2], kB[2];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const float *pc = prm + c0 + 8 * k + 2 * q;
-      kA3[k] = make_float2(pc[0], pc[1]); kZ3[k] = make_float2(pc[64], pc[65]); kAd[k] = make_float2(pc[128], pc[129]);
-      kZd[k] = make_float2(pc[192], pc[193]); kB[k] = make_float2(pc[256], pc[257]);
-    }
     const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    const int c0 = slice * 16;
     const bool want_rs = kQuant && a.out_rowsum != nullptr;
     for (int i = 0; i < count; ++i) {
       const int p = i & 1, t = i >> 1;          // pipeline / accumulator, and its tile ordinal
       const int m_tile = first_m + i * per_n;
+      const long long m = (long long)m_tile * kTileM + row;
+      const bool valid = m < a.M;
       const uint32_t tcol = tlane + p * kBtAccCols;
       mbar_wait(tfull_bar(p), (uint32_t)(t & 1));
       tc_fence_after();
-      // x[h][e + 2 v + 4 k] = element (row 16 h + 8 v + g, column c0 + 8 k + 2 q + e) of the quarter's 32 x 16 block
-      uint32_t a3[2][8], lo[2][8], hi[2][8];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint32_t th = tcol + ((uint32_t)(16 * h) << 16);
-        tmem_ld16x256b_x2(th + c0, a3[h]);
-        tmem_ld16x256b_x2(th + kBtN3 + c0, lo[h]);
-        tmem_ld16x256b_x2(th + kBtN3 + 64 + c0, hi[h]);
-      }
-      const uint32_t s3_lane = tmem_ld1(tcol + 64);           // 32x32b: this lane's row
-      const uint32_t sd_lane = tmem_ld1(tcol + kBtN3 + 128);
+      uint32_t a3[16], lo[16], hi[16];
+      tmem_ld16(tcol + c0, a3);
+      tmem_ld16(tcol + kBtN3 + c0, lo);
+      tmem_ld16(tcol + kBtN3 + 64 + c0, hi);
+      const float S3 = (float)(int)tmem_ld1(tcol + 64);
+      const float Sd = (float)(int)tmem_ld1(tcol + kBtN3 + 128);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(tempty_bar(p));  // everything of this tile is in registers: the pipeline's next MMAs may start
-      const uint32_t stg = smem_base + a.out_off + (uint32_t)(i % kBtStage) * (kTileM * 64);
-      volatile uint32_t *rs_scratch = rs_base + (i & 1) * 512;  // tile i + 1 must not overwrite what tile i still reads
+      uint32_t pk[4];
+      float *of = reinterpret_cast<float *>(a.out) + m * a.Cout + my_n * 64 + c0;
 #pragma unroll
-      for (int ri = 0; ri < 4; ++ri) {            // row 8 ri + g of the quarter
-        const int h = ri >> 1, v = ri & 1;
-        const float S3 = (float)(int)__shfl_sync(0xffffffffu, s3_lane, 8 * ri + g);
-        const float Sd = (float)(int)__shfl_sync(0xffffffffu, sd_lane, 8 * ri + g);
-        const int row = wq * 32 + 8 * ri + g;
-        const long long m = (long long)m_tile * kTileM + row;
-        float2 y[2];
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const uint32_t pofs = prm_s + (uint32_t)q4 * 16;
+        const uint4 pa3 = lds128(pofs), pz3 = lds128(pofs + 256), pad = lds128(pofs + 512), pzd = lds128(pofs + 768),
+                    pb = lds128(pofs + 1024);
+        const uint32_t va3[4] = {pa3.x, pa3.y, pa3.z, pa3.w}, vz3[4] = {pz3.x, pz3.y, pz3.z, pz3.w};
+        const uint32_t vad[4] = {pad.x, pad.y, pad.z, pad.w}, vzd[4] = {pzd.x, pzd.y, pzd.z, pzd.w};
+        const uint32_t vb[4] = {pb.x, pb.y, pb.z, pb.w};
+        float v[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int j = 2 * v + 4 * k;
-          const float2 f3 = make_float2((float)(int)a3[h][j], (float)(int)a3[h][j + 1]);
-          const float2 fd = ffma2(make_float2((float)(int)hi[h][j], (float)(int)hi[h][j + 1]), make_float2(256.0f, 256.0f),
-                                  make_float2((float)(int)lo[h][j], (float)(int)lo[h][j + 1]));
-          float2 yy = ffma2(make_float2(S3, S3), kZ3[k], kB[k]);
-          yy = ffma2(make_float2(Sd, Sd), kZd[k], yy);
-          yy = ffma2(f3, kA3[k], yy);
-          y[k] = ffma2(fd, kAd[k], yy);
+        for (int b = 0; b < 4; b += 2) {
+          const int j = 4 * q4 + b;
+          const float2 f3 = make_float2((float)(int)a3[j], (float)(int)a3[j + 1]);
+          const float2 fd = ffma2(make_float2((float)(int)hi[j], (float)(int)hi[j + 1]), make_float2(256.0f, 256.0f),
+                                  make_float2((float)(int)lo[j], (float)(int)lo[j + 1]));
+          float2 y = ffma2(make_float2(S3, S3), make_float2(__uint_as_float(vz3[b]), __uint_as_float(vz3[b + 1])),
+                           make_float2(__uint_as_float(vb[b]), __uint_as_float(vb[b + 1])));
+          y = ffma2(make_float2(Sd, Sd), make_float2(__uint_as_float(vzd[b]), __uint_as_float(vzd[b + 1])), y);
+          y = ffma2(f3, make_float2(__uint_as_float(va3[b]), __uint_as_float(va3[b + 1])), y);
+          y = ffma2(fd, make_float2(__uint_as_float(vad[b]), __uint_as_float(vad[b + 1])), y);
+          v[b] = y.x; v[b + 1] = y.y;
         }
         if (!kQuant) {
-          if (m < a.M) {
-            float *of = reinterpret_cast<float *>(a.out) + m * a.Cout + my_n * 64 + c0 + 2 * q;
-            *reinterpret_cast<float2 *>(of) = make_float2(fmaxf(y[0].x, 0.f), fmaxf(y[0].y, 0.f));
-            *reinterpret_cast<float2 *>(of + 8) = make_float2(fmaxf(y[1].x, 0.f), fmaxf(y[1].y, 0.f));
-          }
+          if (valid) reinterpret_cast<float4 *>(of)[q4] = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
         } else {
-          const uint32_t w = epi_pack4<false>(y[0].x, y[0].y, y[1].x, y[1].y);  // saturation at 0 is the ReLU
-          // bytes 2 q, 2 q + 1 of the row's two 8-byte groups inside the slice's 16-byte chunk
-          const uint32_t chunk = stg + (uint32_t)(row * 64) + ((((uint32_t)slice) ^ ((uint32_t)(row >> 1) & 3u)) << 4) + 2u * q;
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(chunk), "h"((uint16_t)(w & 0xffffu)) : "memory");
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(chunk + 8u), "h"((uint16_t)(w >> 16)) : "memory");
-          if (want_rs) {
-            uint32_t rsum = __dp4a(w, 0x01010101u, 0u);
-            rsum += __shfl_xor_sync(0xffffffffu, rsum, 1);
-            rsum += __shfl_xor_sync(0xffffffffu, rsum, 2);
-            if (q == 0) rs_scratch[slice * 128 + row] = rsum;
-          }
+          pk[q4] = epi_pack4<false>(v[0], v[1], v[2], v[3]);  // saturation at 0 is the ReLU
         }
       }
       if (kQuant) {
+        const uint32_t stg = smem_base + a.out_off + (uint32_t)(i % kBtStage) * (kTileM * 64);
+        sts128(stg + row_byte + (((uint32_t)slice ^ row_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        uint32_t rsum = 0;
+        volatile uint32_t *rs_scratch = rs_base + (i & 1) * 384;  // tile i + 1 must not overwrite what tile i still reads
+        if (want_rs) {
+          rsum = __dp4a(pk[0], 0x01010101u, __dp4a(pk[1], 0x01010101u, __dp4a(pk[2], 0x01010101u, __dp4a(pk[3], 0x01010101u, 0u))));
+          if (slice != 0) rs_scratch[(slice - 1) * 128 + row] = rsum;
+        }
         fence_proxy_async_smem();
         named_bar_sync(1, kBtCrew);
         if (et == 0) {
@@ -317,11 +304,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
           // (i + 1 - kBtStage = i - 2) is free before this thread reaches the next barrier
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
-        if (want_rs && slice == 0) {   // 128 threads, one pixel each: the four slices' sums of the pixel's channels
-          const int row = wq * 32 + lane;
-          const long long m = (long long)m_tile * kTileM + row;
-          if (m < a.M)
-            a.out_rowsum[(long long)my_n * a.M + m] = rs_scratch[row] + rs_scratch[128 + row] + rs_scratch[256 + row] + rs_scratch[384 + row];
+        if (want_rs && slice == 0) {
+          if (valid) a.out_rowsum[(long long)my_n * a.M + m] = rsum + rs_scratch[row] + rs_scratch[128 + row] + rs_scratch[256 + row];
         }
       }
     }
@@ -454,7 +438,7 @@ using namespace slq;
 static int bt_plan(const slq_blocktail_desc *d, int swz, int *stages, int off[6]) {
   const int k3 = d->Cmid / swz, kd = d->Cin / swz;
   const int b3 = k3 * kBtN3 * swz, bd = kd * kBtNd * swz;
-  const int fixed = b3 + bd + kBtStage * kTileM * 64 + (5 * 64 * 4 + 2 * 4 * 128 * 4) + 512 + 1024;
+  const int fixed = b3 + bd + kBtStage * kTileM * 64 + (5 * 64 * 4 + 2 * 3 * 128 * 4) + 512 + 1024;
   const int a_bytes = kTileM * swz;
   int st = std::min(kBtMaxStages, (232448 - fixed) / (2 * a_bytes));
   if (st < 2) return -1;
@@ -464,7 +448,7 @@ static int bt_plan(const slq_blocktail_desc *d, int swz, int *stages, int off[6]
   off[2] = b3 + bd;                  // ring (both pipelines)
   off[3] = off[2] + 2 * st * a_bytes;  // output staging
   off[4] = off[3] + kBtStage * kTileM * 64;   // constants + row-sum scratch
-  off[5] = off[4] + 5 * 64 * 4 + 2 * 4 * 128 * 4;  // barriers
+  off[5] = off[4] + 5 * 64 * 4 + 2 * 3 * 128 * 4;  // barriers
   return 1024 + off[5] + 512;
 }
 

@@ -446,7 +446,7 @@ constexpr int kTsMaxRowBytes = 1024;              // W <= 256 fp32 elements
 constexpr int kTsStageBytes = 6 * kTsMaxRowBytes; // one pair: 3 channels x 2 rows, raw
 constexpr int kTsStageOff = 0;
 constexpr int kTsRowBufOff = kTsStageOff + kTsSlots * kTsStageBytes;
-constexpr int kTsRowBufBytes = 2 * 6 * kTsRowP * 2;   // double-buffered fp16 rows of one pair
+constexpr int kTsRowBufBytes = 4 * 6 * kTsRowP * 2;   // fp16 rows of one pair: two buffers per builder group
 constexpr int kTsBOff = ((kTsRowBufOff + kTsRowBufBytes + 1023) / 1024) * 1024;
 constexpr int kTsConvOff = kTsBOff + kSfBBytes;
 constexpr int kTsPrmOff = kTsConvOff + kSfConvRing * kSfConvRowBytes;
@@ -455,7 +455,7 @@ constexpr int kTsSmemBytes = 1024 + kTsBarOff + 512;
 constexpr int kTsBuildW = 8, kTsMmaW = 2, kTsEpiW = 16, kTsPoolW = 4;
 constexpr int kTsWarps = 1 + kTsBuildW + kTsMmaW + kTsEpiW + kTsPoolW;  // producer + builders + MMA + epilogue + pool = 31
 constexpr int kTsThreads = kTsWarps * 32;
-constexpr int kTsBuilders = kTsBuildW * 32, kTsEpi = kTsEpiW * 32;
+constexpr int kTsGroupW = kTsBuildW / 2, kTsGroup = kTsGroupW * 32, kTsEpi = kTsEpiW * 32;  // two builder groups of 4 warps
 constexpr int kTsAccCols = 64, kTsSlabBase = 256, kTsSlotCols = 24;
 constexpr int kTsTmemCols = 512;
 static_assert(kTsSmemBytes <= 232448, "stem v2 exceeds 227 KB of shared memory");
@@ -515,8 +515,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
   if (threadIdx.x == 0) {
     for (int s = 0; s < kTsSlots; ++s) {
       mbar_init(sfull_bar(s), 1);
-      mbar_init(sempty_bar(s), kTsBuildW);
-      mbar_init(pfull_bar(s), kTsBuildW);
+      mbar_init(sempty_bar(s), kTsGroupW);
+      mbar_init(pfull_bar(s), kTsGroupW);
       mbar_init(pfree_bar(s), 4);
     }
     for (int b = 0; b < 4; ++b) {
@@ -582,9 +582,13 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     }
   } else if (warp <= kTsBuildW) {
     // ================================ builders ================================================
-    const int bt = threadIdx.x - 32;                 // 0..255
+    // Two groups of four warps (one warp per TMEM lane quarter), pair g -> group g & 1: while one group writes its
+    // pair's slabs to tensor memory the other converts the next pair -- a pair's chain (wait, convert, barrier,
+    // wait for the slot, six tcgen05.st, wait::st, arrive) is ~1500 cycles of mostly latency, and with all eight
+    // warps walking it together it was the pace of the whole kernel.
+    const int group = (warp - 1) >> 2;
+    const int bt = threadIdx.x - 32 - group * kTsGroup;  // 0..127 inside the group
     const int quarter = warp & 3;                    // the TMEM lanes this warp may touch
-    const int sub = (warp - 1) >> 2;                 // which three of the six (c, j) rows of a pair it writes
     const int q = quarter * 32 + lane;               // output column == TMEM lane
     __half *rowbuf = reinterpret_cast<__half *>(smem + kTsRowBufOff);
     const int w4 = a.W >> 2;                         // 4-element groups per row (<= 64)
@@ -593,18 +597,20 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
       int n, j0, j1, p0, p1;
       unit_rows(a, u, n, j0, j1, p0, p1);
       for (int t = p0 - 2; t <= p1; ++t, ++g) {
+        if ((g & 1) != group) continue;
         const int s = g & (kTsSlots - 1);
         const uint32_t ph = (uint32_t)((g >> 3) & 1);
-        __half *rb = rowbuf + (g & 1) * 6 * kTsRowP;
-        if (bt == 0) stem_trace(a, 1, tn, 2, g);
+        __half *rb = rowbuf + (group * 2 + ((g >> 1) & 1)) * 6 * kTsRowP;
+        const int tr = group ? 8 : 1;  // trace issuer
+        if (bt == 0) stem_trace(a, tr, tn, 2, g);
         mbar_wait(sfull_bar(s), ph);
-        if (bt == 0) stem_trace(a, 1, tn, 3, g);
-        // 1. raw -> fp16, every element once: thread = (row r6 of the six, 4-element group c4); two passes
+        if (bt == 0) stem_trace(a, tr, tn, 3, g);
+        // 1. raw -> fp16, every element once: thread = (row r6 of the six, 4-element group c4); three passes
         const uint8_t *stg = smem + kTsStageOff + s * kTsStageBytes;
 #pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-          const int r6 = pass * 4 + (bt >> 6), c4 = bt & 63;
-          if (r6 >= 6 || c4 >= w4 || (SF_DBG(a) & 1)) continue;
+        for (int pass = 0; pass < 3; ++pass) {
+          const int r6 = pass * 2 + (bt >> 6), c4 = bt & 63;
+          if (c4 >= w4 || (SF_DBG(a) & 1)) continue;
           const int c = r6 >> 1;
           float f[4];
           const uint8_t *src = stg + r6 * row_bytes + c4 * 4 * ESZ;  // rows outside the image arrive as zeros
@@ -627,18 +633,18 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
           *reinterpret_cast<__half2 *>(dst + 1) = __floats2half2_rn(f[1], f[2]);
           dst[3] = __float2half_rn(f[3]);
         }
-        named_bar_sync(1, kTsBuilders);  // rows complete; also: nobody still reads the buffer of pair g - 2
+        named_bar_sync(1 + group, kTsGroup);  // rows complete; also: nobody in the group still reads the buffer of pair g - 4
         if (lane == 0) mbar_arrive(sempty_bar(s));  // the staging slot may be refilled
         // 2. the pair's TMEM slot must be free: the four conv rows that used pair g - 8 have completed
-        if (bt == 0) stem_trace(a, 1, tn, 4, g);
+        if (bt == 0) stem_trace(a, tr, tn, 4, g);
         if (g >= kTsSlots) mbar_wait(pfree_bar(s), ph ^ 1);
-        if (bt == 0) stem_trace(a, 1, tn, 5, g);
+        if (bt == 0) stem_trace(a, tr, tn, 5, g);
         tc_fence_after();
         // 3. this thread's 16-byte windows x[c][h][2q-3 .. 2q+4] -> the slab's TMEM columns
         const uint32_t tslab = tmem_base + ((uint32_t)(quarter * 32) << 16) + kTsSlabBase + s * kTsSlotCols;
 #pragma unroll
-        for (int k = 0; k < 3 && !(SF_DBG(a) & 2); ++k) {
-          const int r6 = sub * 3 + k;  // = c * 2 + j
+        for (int k = 0; k < 6 && !(SF_DBG(a) & 2); ++k) {
+          const int r6 = k;  // = c * 2 + j
           const uint32_t *src = reinterpret_cast<const uint32_t *>(rb + r6 * kTsRowP + 2 * q);
           tmem_st4(tslab + (r6 >> 1) * 8 + (r6 & 1) * 4, src[0], src[1], src[2], src[3]);
         }
@@ -646,7 +652,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(pfull_bar(s));
-        if (bt == 0) stem_trace(a, 1, tn, 6, g);
+        if (bt == 0) stem_trace(a, tr, tn, 6, g);
       }
     }
   } else if (warp <= kTsBuildW + kTsMmaW) {
@@ -666,7 +672,8 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         if (lane == 0) stem_trace(a, 2 + mw, tn, 7, rc);
         if (rc >= 4) mbar_wait(tempty_bar(acc), (uint32_t)(((rc >> 2) & 1) ^ 1));
         if (lane == 0) stem_trace(a, 2 + mw, tn, 8, rc);
-        // pairs complete in order: the newest one implies the three before it
+        // each builder group completes its pairs in order: the newest pair of either group implies the older ones
+        mbar_wait(pfull_bar((g_lo + 2) & (kTsSlots - 1)), (uint32_t)(((g_lo + 2) >> 3) & 1));
         mbar_wait(pfull_bar((g_lo + 3) & (kTsSlots - 1)), (uint32_t)(((g_lo + 3) >> 3) & 1));
         tc_fence_after();
         if (lane == 0) stem_trace(a, 2 + mw, tn, 9, rc);

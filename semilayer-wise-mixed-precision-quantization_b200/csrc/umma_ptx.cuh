@@ -179,13 +179,6 @@ __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
   if constexpr (N == 32) tmem_ld32(taddr, r);
   else tmem_ld16(taddr, r);
 }
-// 16 lanes x 16 columns in the mma-fragment layout: lane 4 g + q receives r[e + 2 v + 4 k] = element
-// (lane base + 8 v + g, column base + 8 k + 2 q + e), e, v, k in {0, 1}
-__device__ __forceinline__ void tmem_ld16x256b_x2(uint32_t taddr, uint32_t (&r)[8]) {
-  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr));
-}
 __device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
   uint32_t v;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
