@@ -61,7 +61,10 @@ struct BtArgs {
   int in3_id, ind_id, out_id, out_mode;
   void *out;
   uint32_t *out_rowsum;
+  int dbg;  // $SLQ_BT_DBG (debug build only, timing experiments): 1 no constant loads, 2 no limb TMEM loads, 4 no staging /
+            // store, 8 no downsample MMAs, 32 no epilogue arithmetic
 };
+#define BT_DBG(a) (kDebugTrace ? (a).dbg : 0)
 
 // per-channel constants of the fused epilogue, structure of arrays in shared memory (64 channels):
 //   A3 = wscale3 * s_y2 [* inv] ; Z3 = zf3 * A3 ; Ad = wscaled * s_x [* inv] ; Zd = zfd * Ad ; B = (bias3 + biasd) [* inv]
@@ -208,7 +211,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
                                                                    : a.bd_off + (kb - a.k3_blocks) * (kBtNd * SWZ)));
           const bool first = is3 ? kb == 0 : kb == a.k3_blocks;  // first K block of its accumulator
 #pragma unroll
-          for (int k = 0; k < SWZ / 32; ++k)
+          for (int k = 0; k < SWZ / 32 && !(!is3 && (BT_DBG(a) & 8)); ++k)
             umma_i8(tmem_u + (is3 ? 0 : kBtN3), da + 2 * k, db + 2 * k, is3 ? idesc3 : idescd, (uint32_t)(!first || k != 0));
           umma_commit(empty_bar(p, s));
           if (kb == kb_tile - 1) umma_commit(tfull_bar(p));
@@ -249,8 +252,13 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       tc_fence_after();
       uint32_t a3[16], lo[16], hi[16];
       tmem_ld16(tcol + c0, a3);
-      tmem_ld16(tcol + kBtN3 + c0, lo);
-      tmem_ld16(tcol + kBtN3 + 64 + c0, hi);
+      if (!(BT_DBG(a) & 2)) {
+        tmem_ld16(tcol + kBtN3 + c0, lo);
+        tmem_ld16(tcol + kBtN3 + 64 + c0, hi);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { lo[j] = a3[(j + 1) & 15]; hi[j] = a3[(j + 2) & 15]; }
+      }
       const float S3 = (float)(int)tmem_ld1(tcol + 64);
       const float Sd = (float)(int)tmem_ld1(tcol + kBtN3 + 128);
       tmem_ld_wait();
@@ -261,8 +269,12 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const uint32_t pofs = prm_s + (uint32_t)q4 * 16;
-        const uint4 pa3 = lds128(pofs), pz3 = lds128(pofs + 256), pad = lds128(pofs + 512), pzd = lds128(pofs + 768),
-                    pb = lds128(pofs + 1024);
+        uint4 pa3, pz3, pad, pzd, pb;
+        if (!(BT_DBG(a) & 1)) {
+          pa3 = lds128(pofs); pz3 = lds128(pofs + 256); pad = lds128(pofs + 512); pzd = lds128(pofs + 768); pb = lds128(pofs + 1024);
+        } else {
+          pa3 = pz3 = pad = pzd = pb = make_uint4(0x3a000000u + q4, 0x3a100000u, 0x3a200000u, 0x3a300000u);
+        }
         const uint32_t va3[4] = {pa3.x, pa3.y, pa3.z, pa3.w}, vz3[4] = {pz3.x, pz3.y, pz3.z, pz3.w};
         const uint32_t vad[4] = {pad.x, pad.y, pad.z, pad.w}, vzd[4] = {pzd.x, pzd.y, pzd.z, pzd.w};
         const uint32_t vb[4] = {pb.x, pb.y, pb.z, pb.w};
@@ -280,6 +292,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
           y = ffma2(fd, make_float2(__uint_as_float(vad[b]), __uint_as_float(vad[b + 1])), y);
           v[b] = y.x; v[b + 1] = y.y;
         }
+        if (BT_DBG(a) & 32) { v[0] = __uint_as_float(a3[4 * q4] ^ lo[4 * q4]); v[1] = v[2] = v[3] = __uint_as_float(hi[4 * q4]); }
         if (!kQuant) {
           if (valid) reinterpret_cast<float4 *>(of)[q4] = make_float4(fmaxf(v[0], 0.f), fmaxf(v[1], 0.f), fmaxf(v[2], 0.f), fmaxf(v[3], 0.f));
         } else {
@@ -288,7 +301,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       }
       if (kQuant) {
         const uint32_t stg = smem_base + a.out_off + (uint32_t)(i % kBtStage) * (kTileM * 64);
-        sts128(stg + row_byte + (((uint32_t)slice ^ row_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        if (!(BT_DBG(a) & 4)) sts128(stg + row_byte + (((uint32_t)slice ^ row_sw) << 4), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+        else if ((pk[0] ^ pk[1] ^ pk[2] ^ pk[3]) == 0x12345679u) sts128(stg, make_uint4(pk[0], pk[1], pk[2], pk[3]));
         uint32_t rsum = 0;
         volatile uint32_t *rs_scratch = rs_base + (i & 1) * 384;  // tile i + 1 must not overwrite what tile i still reads
         if (want_rs) {
@@ -297,7 +311,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
         }
         fence_proxy_async_smem();
         named_bar_sync(1, kBtCrew);
-        if (et == 0) {
+        if (et == 0 && !(BT_DBG(a) & 4)) {
           tma_store_2d(&tmO, stg, my_n * 64, m_tile * kTileM);
           tma_store_commit();
           // at most the two newest stores still read their staging tiles: the tile that tile i + 1 overwrites
@@ -544,6 +558,10 @@ extern "C" int slq_blocktail_launch(slq_blocktail *h, const slq_blocktail_epilog
   a.wscale3 = e->wscale3; a.zf3 = e->zf3; a.bias3 = e->bias3; a.wscaled = e->wscaled; a.zfd = e->zfd; a.biasd = e->biasd;
   a.act_scales = e->act_scales; a.in3_id = e->in3_id; a.ind_id = e->ind_id; a.out_id = e->out_id; a.out_mode = e->out_mode;
   a.out = e->out; a.out_rowsum = e->out_mode == SLQ_OUT_U8 ? e->out_rowsum : nullptr;
+  a.dbg = 0;
+#if SLQ_DEBUG_TRACE
+  if (const char *d = getenv("SLQ_BT_DBG")) a.dbg = atoi(d);
+#endif
   cudaStream_t st = (cudaStream_t)stream;
   if (d.impl == SLQ_IMPL_SIMT) {
     dim3 grid((unsigned)ceil_div(h->M, 4), (unsigned)ceil_div(d.Cout, 32));
