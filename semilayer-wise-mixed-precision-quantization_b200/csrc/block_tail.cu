@@ -123,7 +123,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
     for (int p = 0; p < 2; ++p) {
       for (int s = 0; s < a.stages; ++s) { mbar_init(full_bar(p, s), 1); mbar_init(empty_bar(p, s), 1); }
       mbar_init(tfull_bar(p), 1);
-      mbar_init(tempty_bar(p), kBtCrew);
+      mbar_init(tempty_bar(p), kBtCrew / 32);  // one arrival per crew warp
     }
     mbar_init(bfull_bar, 1);
     fence_barrier_init();
@@ -263,7 +263,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       const float Sd = (float)(int)tmem_ld1(tcol + kBtN3 + 128);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(tempty_bar(p));  // everything of this tile is in registers: the pipeline's next MMAs may start
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(p));  // everything of this tile is in registers: the pipeline's next MMAs may start
       uint32_t pk[4];
       float *of = reinterpret_cast<float *>(a.out) + m * a.Cout + my_n * 64 + c0;
 #pragma unroll

@@ -297,12 +297,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int b = 0; b < kTileBars; ++b) {
       mbar_init(tfull_bar(b), (uint32_t)a.mma_warps_per_tile);
-      mbar_init(tempty_bar(b), kTeam);
+      mbar_init(tempty_bar(b), kTeam / 32);  // one arrival per epilogue warp of the team
       mbar_init(tstart_bar(b), 1);
     }
     for (int b = 0; b < sp.res_bufs; ++b) {
       mbar_init(rfull_bar(b), 1);
-      mbar_init(rempty_bar(b), kTeam);
+      mbar_init(rempty_bar(b), kTeam / 32);
     }
     mbar_init(bfull_bar, 1);
     mbar_init(bready_bar, 2 * kTeam);
@@ -838,8 +838,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (want_rs && half == 1) rs_scratch[row] = rsum;  // the other half of the tile's channels adds it below
       tc_fence_before();
       if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 6, (int)it);
-      mbar_arrive(tempty_bar(tb));  // kTeam arrivals release the accumulator buffer
-      if (has_res) mbar_arrive(rempty_bar(rbuf));
+      // ONE arrival per warp (an mbarrier arrive is a shared-memory atomic: 256 of them per tile and barrier,
+      // serialised on the barrier's word, were the largest single cost of the epilogue-bound layers)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(tempty_bar(tb));  // kTeam / 32 arrivals release the accumulator buffer
+        if (has_res) mbar_arrive(rempty_bar(rbuf));
+      }
       if (kWide || !a.tma_out) {
         if (want_rs) named_bar_sync(1 + team, kTeam);  // the scratch row sums are visible
       } else {

@@ -33,6 +33,7 @@
 struct slq_stem {
   int N, H, W, Hc, Wc, Hp, Wp;
   __half *wh;  // [64, 192] fp16, zero padded; K order of the kernel in use (see the two weight kernels)
+  float *wf;   // the same matrix in fp32 (stem_ts_kernel folds the BN scale into it before rounding to fp16)
   int num_ctas;
   int use_ts;  // 1: stem_ts_kernel (A operand in TMEM; needs 16-byte input rows: W % 16 == 0), 0: stem_fused_kernel
 };
@@ -81,6 +82,7 @@ struct StemArgs {
   float nmean[3], nstd[3];  // u8 input: value = (u/255 - mean[c]) / std[c]  (imagenet.py:14-15 ToTensor + Normalize)
   int N, H, W, Hc, Wc, Hp, Wp;
   const __half *wh;
+  const float *wf;
   const float *bn_a, *bn_b, *act_scales;
   int out_id, out_mode;
   void *out;  // u8 pooled [N,Hp,Wp,64]  |  fp32 conv rows [N,Hc,Wc,64] (SLQ_OUT_F32)
@@ -462,14 +464,14 @@ static_assert(kTsSmemBytes <= 232448, "stem v2 exceeds 227 KB of shared memory")
 
 // w fp32 [64, 3, 7, 7] -> wh fp16 [64, 192]: wh[oc][c*64 + ch*8 + s] = w[oc][c][ch-1][s]  (ch = 2i + j is
 // the row of pair i: filter row r = ch - 1; ch = 0 and s = 7 are zero)
-__global__ void stem_weights_ts_kernel(const float *__restrict__ w, __half *__restrict__ wh) {
+__global__ void stem_weights_ts_kernel(const float *__restrict__ w, float *__restrict__ wh) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 64 * kSfK) return;
   const int k = idx % kSfK, oc = idx / kSfK;
   const int c = k >> 6, ch = (k >> 3) & 7, s = k & 7;
   float v = 0.f;
   if (ch >= 1 && s < 7) v = w[((oc * 3 + c) * 7 + (ch - 1)) * 7 + s];
-  wh[idx] = __float2half_rn(v);
+  wh[idx] = v;
 }
 
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -540,15 +542,22 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     reinterpret_cast<uint4 *>(smem + kTsRowBufOff)[i] = make_uint4(0, 0, 0, 0);
   for (int i = threadIdx.x; i < 64 * kSfChunks; i += blockDim.x) {
     const int oc = i / kSfChunks, j = i % kSfChunks;
-    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(a.wh + oc * kSfK + j * 8));
+    // the BN scale of the output channel goes into the weights BEFORE they are rounded to fp16 (one rounding, like
+    // the plain fp16 weights had): the epilogue is then y = acc * inv + b' with a scalar inv and 16 per-channel b'
+    // that stay in registers -- no constant loads in its loop
+    const float4 w0 = __ldg(reinterpret_cast<const float4 *>(a.wf + oc * kSfK + j * 8));
+    const float4 w1 = __ldg(reinterpret_cast<const float4 *>(a.wf + oc * kSfK + j * 8 + 4));
+    const float sa = a.bn_a[oc];
+    const __half2 h0 = __floats2half2_rn(__fmul_rn(w0.x, sa), __fmul_rn(w0.y, sa)), h1 = __floats2half2_rn(__fmul_rn(w0.z, sa), __fmul_rn(w0.w, sa));
+    const __half2 h2 = __floats2half2_rn(__fmul_rn(w1.x, sa), __fmul_rn(w1.y, sa)), h3 = __floats2half2_rn(__fmul_rn(w1.z, sa), __fmul_rn(w1.w, sa));
+    const uint4 v = make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                               *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
     const int kb = j >> 3, cj = j & 7;  // kb = channel c, cj = 2i + j: 32 bytes per pair i inside the 128-byte row
     *reinterpret_cast<uint4 *>(smem + kTsBOff + kb * 8192 + oc * 128 + ((cj ^ (oc & 7)) << 4)) = v;
   }
-  if (threadIdx.x < 64) {  // u8 output: the re-quantisation multiply is folded into the BN constants
-    const float inv = a.out_mode == SLQ_OUT_F32 ? 1.f : __fdiv_rn(1.0f, a.act_scales[a.out_id]);
-    reinterpret_cast<float2 *>(smem + kTsPrmOff)[threadIdx.x] =
-        make_float2(__fmul_rn(a.bn_a[threadIdx.x], inv), __fmul_rn(a.bn_b[threadIdx.x], inv));
-  }
+  const float inv_out = a.out_mode == SLQ_OUT_F32 ? 1.f : __fdiv_rn(1.0f, a.act_scales[a.out_id]);
+  if (threadIdx.x < 64)  // u8 output: in units of the output scale
+    reinterpret_cast<float *>(smem + kTsPrmOff)[threadIdx.x] = __fmul_rn(a.bn_b[threadIdx.x], inv_out);
   fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -712,7 +721,10 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
     // the per-row chain wait -> tcgen05.ld -> convert -> pack of these warps is what paced the whole kernel
     const int wq = warp & 3, sl = (warp - (1 + kTsBuildW + kTsMmaW)) >> 2;
     const int q = wq * 32 + lane;
-    const float2 *prm = reinterpret_cast<const float2 *>(smem + kTsPrmOff);
+    float2 kb2[8];  // b' of this thread's 16 channels, for the CTA's whole life
+#pragma unroll
+    for (int j = 0; j < 8; ++j) kb2[j] = reinterpret_cast<const float2 *>(smem + kTsPrmOff)[sl * 8 + j];
+    const float2 inv2 = make_float2(inv_out, inv_out);
     uint8_t *cring = smem + kTsConvOff;
     const bool f32_out = a.out_mode == SLQ_OUT_F32;
     uint32_t vm[4] = {0, 0, 0, 0};  // running vertical maximum of the pooling window (packed u8)
@@ -737,9 +749,7 @@ __global__ void __launch_bounds__(kTsThreads, 1) stem_ts_kernel(const __grid_con
         float y[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float4 p4 = *reinterpret_cast<const float4 *>(&prm[sl * 16 + j]);  // {a0, b0, a1, b1}
-          const float2 r = ffma2(make_float2(__uint_as_float(av[j]), __uint_as_float(av[j + 1])),
-                                 make_float2(p4.x, p4.z), make_float2(p4.y, p4.w));  // u8: in units of the output scale
+          const float2 r = ffma2(make_float2(__uint_as_float(av[j]), __uint_as_float(av[j + 1])), inv2, kb2[j >> 1]);
           y[j] = r.x; y[j + 1] = r.y;
         }
         if (f32_out) {
@@ -856,7 +866,7 @@ static void stem_dims(int H, int W, int *Hc, int *Wc, int *Hp, int *Wp) {
 
 extern "C" int64_t slq_stem_workspace_bytes(int32_t N, int32_t H, int32_t W) {
   if (N <= 0 || H < 7 || W < 7) return -1;
-  return 64 * kSfK * 2;  // the fp16 weight matrix; activations never leave the SM
+  return 64 * kSfK * (2 + 4);  // the weight matrix in fp16 and in fp32; activations never leave the SM
 }
 
 extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace, slq_stem **out) {
@@ -873,6 +883,7 @@ extern "C" int slq_stem_create(int32_t N, int32_t H, int32_t W, void *workspace,
     return SLQ_ERR_UNSUPPORTED;
   }
   s->wh = reinterpret_cast<__half *>(workspace);
+  s->wf = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(workspace) + 64 * kSfK * 2);
   s->use_ts = (W % 16 == 0) ? 1 : 0;
 #if SLQ_DEBUG_TRACE
   if (getenv("SLQ_STEM_OLD")) s->use_ts = 0;  // A/B timing of the round-1 kernel (debug build only)
@@ -908,7 +919,7 @@ extern "C" void slq_stem_destroy(slq_stem *s) { delete s; }
 
 extern "C" int slq_stem_set_weights(slq_stem *s, const float *w, void *stream) {
   SLQ_CHECK_ARG(s && w, "slq_stem_set_weights: null pointer argument");
-  if (s->use_ts) stem_weights_ts_kernel<<<(64 * kSfK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wh);
+  if (s->use_ts) stem_weights_ts_kernel<<<(64 * kSfK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wf);
   else stem_weights_kernel<<<(64 * kSfK + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, s->wh);
   SLQ_LAUNCH_CHECK();
   return SLQ_OK;
@@ -939,6 +950,7 @@ extern "C" int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, c
   }
   a.N = s->N; a.H = s->H; a.W = s->W; a.Hc = s->Hc; a.Wc = s->Wc; a.Hp = s->Hp; a.Wp = s->Wp;
   a.wh = s->wh;
+  a.wf = s->wf;
   a.bn_a = bn_a; a.bn_b = bn_b; a.act_scales = act_scales; a.out_id = out_id; a.out_mode = out_mode;
   a.out = out_mode == SLQ_OUT_U8 ? out : (void *)f32_scratch;
   a.out_rowsum = out_mode == SLQ_OUT_U8 ? out_rowsum : nullptr;
