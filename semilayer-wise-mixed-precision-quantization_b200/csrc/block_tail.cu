@@ -61,10 +61,18 @@ struct BtArgs {
   int in3_id, ind_id, out_id, out_mode;
   void *out;
   uint32_t *out_rowsum;
+  long long *stats;  // debug build: wait statistics of CTA 0, or NULL
   int dbg;  // $SLQ_BT_DBG (debug build only, timing experiments): 1 no constant loads, 2 no limb TMEM loads, 4 no staging /
             // store, 8 no downsample MMAs, 32 no epilogue arithmetic
 };
 #define BT_DBG(a) (kDebugTrace ? (a).dbg : 0)
+// wait statistics of CTA 0 (debug build, slq_debug_set_trace with a buffer of >= 16 int64): cycles a role spent blocked
+__device__ __forceinline__ void bt_wait(uint32_t bar, uint32_t parity, long long *acc, bool on) {
+  if (!kDebugTrace || !on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  *acc += clock64() - t0;
+}
 
 // per-channel constants of the fused epilogue, structure of arrays in shared memory (64 channels):
 //   A3 = wscale3 * s_y2 [* inv] ; Z3 = zf3 * A3 ; Ad = wscaled * s_x [* inv] ; Zd = zfd * Ad ; B = (bias3 + biasd) [* inv]
@@ -163,6 +171,9 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
     }
     grid_dependency_wait();  // activations of the previous layers
     int c = 0;  // pipeline steps issued by this producer
+    long long w_empty = 0;
+    const bool st_on = kDebugTrace && a.stats != nullptr && blockIdx.x == 0;
+    const long long t_begin = clock64();
     for (int i = p; i < count; i += 2) {
       const int m0 = (first_m + i * per_n) * kTileM;
       int dn = 0, dh = 0, dw = 0;
@@ -175,7 +186,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       }
       for (int kb = 0; kb < kb_tile; ++kb, ++c) {
         const int s = c % a.stages;
-        mbar_wait(empty_bar(p, s), (uint32_t)(((c / a.stages) & 1) ^ 1));
+        bt_wait(empty_bar(p, s), (uint32_t)(((c / a.stages) & 1) ^ 1), &w_empty, st_on);
         if (elect_one()) {
           const uint32_t dst = smem_base + a.ring_off + (p * a.stages + s) * kABytes;
           mbar_expect_tx(full_bar(p, s), kABytes);
@@ -186,6 +197,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
         __syncwarp();
       }
     }
+    if (st_on && lane == 0) { a.stats[p] = w_empty; a.stats[2 + p] = clock64() - t_begin; }
   } else if (warp == 1 || warp == 3) {
     // ================================ MMA issuers ==============================================
     const int p = warp >> 1;
@@ -197,12 +209,15 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       tc_fence_after();
     }
     int c = 0, t = 0;
+    long long w_full = 0, w_tempty = 0;
+    const bool st_on = kDebugTrace && a.stats != nullptr && blockIdx.x == 0;
+    const long long t_begin = clock64();
     for (int i = p; i < count; i += 2, ++t) {
-      if (t >= 1) mbar_wait(tempty_bar(p), (uint32_t)((t - 1) & 1));  // the team drained this pipeline's previous tile
+      if (t >= 1) bt_wait(tempty_bar(p), (uint32_t)((t - 1) & 1), &w_tempty, st_on);  // the crew drained this pipeline's previous tile
       tc_fence_after();
       for (int kb = 0; kb < kb_tile; ++kb, ++c) {
         const int s = c % a.stages;
-        mbar_wait(full_bar(p, s), (uint32_t)((c / a.stages) & 1));
+        bt_wait(full_bar(p, s), (uint32_t)((c / a.stages) & 1), &w_full, st_on);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t da = make_smem_desc<SWZ>(smem_base + a.ring_off + (p * a.stages + s) * kABytes);
@@ -219,6 +234,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
         __syncwarp();
       }
     }
+    if (st_on && lane == 0) { a.stats[4 + p] = w_full; a.stats[6 + p] = w_tempty; a.stats[8 + p] = clock64() - t_begin; }
   } else if (warp >= 4) {
     // ================================ epilogue crew ============================================
     grid_dependency_wait();
@@ -242,13 +258,16 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
     const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
     const int c0 = slice * 16;
     const bool want_rs = kQuant && a.out_rowsum != nullptr;
+    long long w_tfull = 0, w_bar = 0;
+    const bool st_on = kDebugTrace && a.stats != nullptr && blockIdx.x == 0 && et == 0;
+    const long long t_begin = clock64();
     for (int i = 0; i < count; ++i) {
       const int p = i & 1, t = i >> 1;          // pipeline / accumulator, and its tile ordinal
       const int m_tile = first_m + i * per_n;
       const long long m = (long long)m_tile * kTileM + row;
       const bool valid = m < a.M;
       const uint32_t tcol = tlane + p * kBtAccCols;
-      mbar_wait(tfull_bar(p), (uint32_t)(t & 1));
+      bt_wait(tfull_bar(p), (uint32_t)(t & 1), &w_tfull, st_on);
       tc_fence_after();
       uint32_t a3[16], lo[16], hi[16];
       tmem_ld16(tcol + c0, a3);
@@ -311,7 +330,9 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
           if (slice != 0) rs_scratch[(slice - 1) * 128 + row] = rsum;
         }
         fence_proxy_async_smem();
+        const long long tb0 = st_on ? clock64() : 0;
         named_bar_sync(1, kBtCrew);
+        if (st_on) w_bar += clock64() - tb0;
         if (et == 0 && !(BT_DBG(a) & 4)) {
           tma_store_2d(&tmO, stg, my_n * 64, m_tile * kTileM);
           tma_store_commit();
@@ -324,6 +345,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
         }
       }
     }
+    if (st_on) { a.stats[10] = w_tfull; a.stats[11] = w_bar; a.stats[12] = clock64() - t_begin; a.stats[13] = count; }
     if (kQuant && et == 0) tma_store_wait_all();
   }
   tc_fence_before();
@@ -560,7 +582,13 @@ extern "C" int slq_blocktail_launch(slq_blocktail *h, const slq_blocktail_epilog
   a.act_scales = e->act_scales; a.in3_id = e->in3_id; a.ind_id = e->ind_id; a.out_id = e->out_id; a.out_mode = e->out_mode;
   a.out = e->out; a.out_rowsum = e->out_mode == SLQ_OUT_U8 ? e->out_rowsum : nullptr;
   a.dbg = 0;
+  a.stats = nullptr;
 #if SLQ_DEBUG_TRACE
+  {
+    int cap = 0;
+    debug_trace_buffer(&a.stats, &cap);
+    if (cap > -16) a.stats = nullptr;  // statistics mode: slq_debug_set_trace(buf, -16 or below)
+  }
   if (const char *d = getenv("SLQ_BT_DBG")) a.dbg = atoi(d);
 #endif
   cudaStream_t st = (cudaStream_t)stream;

@@ -35,4 +35,17 @@ for cin, cmid, cout, stride, H in [(64, 64, 256, 1, 56), (256, 128, 512, 2, 56),
         e1.record(); torch.cuda.synchronize()
         res.append("dbg=%d %.1f" % (dbg, 1e3 * e0.elapsed_time(e1) / 5))
     print("Cin %d Cmid %d Cout %d s%d H%d: " % (cin, cmid, cout, stride, H) + " | ".join(res) + "  (us per launch)")
+    # where CTA 0's roles wait (cycles blocked in mbarrier waits / the crew barrier, out of each role's loop time)
+    os.environ["SLQ_BT_DBG"] = "0"
+    buf = torch.zeros(64, dtype=torch.int64, device="cuda")
+    lib.slq_debug_set_trace(buf.data_ptr(), -64)
+    L.check(lib.slq_blocktail_launch(h, ctypes.byref(e), L.current_stream()))
+    torch.cuda.synchronize()
+    lib.slq_debug_set_trace(None, 0)
+    st = buf.cpu().numpy()
+    tiles = max(int(st[13]), 1)
+    print("   CTA 0: %d tiles; per tile: producers wait(empty) %d / %d of %d / %d clk | MMA wait(full) %d / %d, wait(tempty) %d / %d of %d / %d | "
+          "crew wait(tfull) %d, barrier %d of %d" % (tiles, st[0] * 2 // tiles, st[1] * 2 // tiles, st[2] * 2 // tiles, st[3] * 2 // tiles,
+                                                    st[4] * 2 // tiles, st[5] * 2 // tiles, st[6] * 2 // tiles, st[7] * 2 // tiles,
+                                                    st[8] * 2 // tiles, st[9] * 2 // tiles, st[10] // tiles, st[11] // tiles, st[12] // tiles))
     lib.slq_blocktail_destroy(h)
