@@ -258,7 +258,8 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
     const uint32_t tlane = tmem_base + ((uint32_t)(wq * 32) << 16);
     const int c0 = slice * 16;
     const bool want_rs = kQuant && a.out_rowsum != nullptr;
-    long long w_tfull = 0, w_bar = 0;
+    long long w_tfull = 0, w_bar = 0, seg[6] = {0, 0, 0, 0, 0, 0}, tseg = 0;
+#define BT_SEG(k) do { if (st_on) { const long long now__ = clock64(); seg[k] += now__ - tseg; tseg = now__; } } while (0)
     const bool st_on = kDebugTrace && a.stats != nullptr && blockIdx.x == 0 && et == 0;
     const long long t_begin = clock64();
     for (int i = 0; i < count; ++i) {
@@ -268,6 +269,7 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       const bool valid = m < a.M;
       const uint32_t tcol = tlane + p * kBtAccCols;
       bt_wait(tfull_bar(p), (uint32_t)(t & 1), &w_tfull, st_on);
+      if (st_on) tseg = clock64();
       tc_fence_after();
       uint32_t a3[16], lo[16], hi[16];
       tmem_ld16(tcol + c0, a3);
@@ -281,9 +283,11 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
       const float S3 = (float)(int)tmem_ld1(tcol + 64);
       const float Sd = (float)(int)tmem_ld1(tcol + kBtN3 + 128);
       tmem_ld_wait();
+      BT_SEG(0);   // TMEM loads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(p));  // everything of this tile is in registers: the pipeline's next MMAs may start
+      BT_SEG(1);   // fence + arrive
       uint32_t pk[4];
       float *of = reinterpret_cast<float *>(a.out) + m * a.Cout + my_n * 64 + c0;
 #pragma unroll
@@ -329,10 +333,13 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
           rsum = __dp4a(pk[0], 0x01010101u, __dp4a(pk[1], 0x01010101u, __dp4a(pk[2], 0x01010101u, __dp4a(pk[3], 0x01010101u, 0u))));
           if (slice != 0) rs_scratch[(slice - 1) * 128 + row] = rsum;
         }
+        BT_SEG(2);   // arithmetic, pack, staging store
         fence_proxy_async_smem();
+        BT_SEG(3);   // proxy fence
         const long long tb0 = st_on ? clock64() : 0;
         named_bar_sync(1, kBtCrew);
         if (st_on) w_bar += clock64() - tb0;
+        BT_SEG(4);   // crew barrier
         if (et == 0 && !(BT_DBG(a) & 4)) {
           tma_store_2d(&tmO, stg, my_n * 64, m_tile * kTileM);
           tma_store_commit();
@@ -343,9 +350,13 @@ block_tail_kernel(const __grid_constant__ CUtensorMap tmA3, const __grid_constan
         if (want_rs && slice == 0) {
           if (valid) a.out_rowsum[(long long)my_n * a.M + m] = rsum + rs_scratch[row] + rs_scratch[128 + row] + rs_scratch[256 + row];
         }
+        BT_SEG(5);   // store issue, wait for the staging tile two tiles back
       }
     }
-    if (st_on) { a.stats[10] = w_tfull; a.stats[11] = w_bar; a.stats[12] = clock64() - t_begin; a.stats[13] = count; }
+    if (st_on) {
+      a.stats[10] = w_tfull; a.stats[11] = w_bar; a.stats[12] = clock64() - t_begin; a.stats[13] = count;
+      for (int k = 0; k < 6; ++k) a.stats[16 + k] = seg[k];
+    }
     if (kQuant && et == 0) tma_store_wait_all();
   }
   tc_fence_before();

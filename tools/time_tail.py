@@ -48,4 +48,6 @@ for cin, cmid, cout, stride, H in [(64, 64, 256, 1, 56), (256, 128, 512, 2, 56),
           "crew wait(tfull) %d, barrier %d of %d" % (tiles, st[0] * 2 // tiles, st[1] * 2 // tiles, st[2] * 2 // tiles, st[3] * 2 // tiles,
                                                     st[4] * 2 // tiles, st[5] * 2 // tiles, st[6] * 2 // tiles, st[7] * 2 // tiles,
                                                     st[8] * 2 // tiles, st[9] * 2 // tiles, st[10] // tiles, st[11] // tiles, st[12] // tiles))
+    print("   crew thread 0, per tile: TMEM loads %d | fence+arrive %d | arithmetic+pack+STS %d | proxy fence %d | crew barrier %d | store issue + wait_group %d clk"
+          % tuple(int(v) // tiles for v in st[16:22]))
     lib.slq_blocktail_destroy(h)
