@@ -164,6 +164,7 @@ struct KernelArgs {
   const int *wgp_seg;          // [n_tiles] bytes of one (n-tile, kb) segment
   const uint16_t *wgp_rowoff;  // [n_tiles][bn_cols + 1] byte offset of every row inside a segment
   long long m_tiles;
+  int half_b;          // debug build: $SLQ_HALF_B experiment (see the producer loop)
   long long *trace;    // debug: CTA 0 logs (event, index, clock) triples here (slq_debug_set_trace)
   int trace_cap;
 };
@@ -443,8 +444,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t fb = full_bar(stage);
       mbar_wait_stat(empty_bar(stage), phase ^ 1, wsum, stats);
       if (tracing && lane == 0) trace_ev(a, tid_, tn, 0, c);
+      // debug build, $SLQ_HALF_B: fetch the weight tile only on every other pipeline step (wrong results; shows how
+      // much of a streamed-weight layer's time is the B traffic through L2)
+      const bool skip_b = kDebugTrace && a.half_b && (c & 2);
       if (elect_one()) {
-        mbar_expect_tx(fb, tx_bytes);
+        mbar_expect_tx(fb, skip_b ? tx_bytes - b_bytes : tx_bytes);
         if (im2col) {
           int cc = cchunk, ts = tap_s, tr = tap_r;
           for (int j = 0; j < grp; ++j) {
@@ -454,7 +458,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           for (int j = 0; j < grp; ++j) tma_load_2d(sa + j * sp.a_bytes, &tmA, fb, (kb0 + j) * SWZ, m0);
         }
-        if (streamed) tma_load_2d(sa + sp.a_bytes, &tmB, fb, kb0 * SWZ, n_tile * bn_cols);
+        if (streamed && !skip_b) tma_load_2d(sa + sp.a_bytes, &tmB, fb, kb0 * SWZ, n_tile * bn_cols);
       }
       __syncwarp();
       if (tracing && lane == 0) trace_ev(a, tid_, tn, 1, c);
@@ -1032,6 +1036,10 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   const int grid = plan_grid(geom, a.sp, sm_count());
   a.trace = g_trace;
   a.trace_cap = g_trace_cap;
+  a.half_b = 0;
+#if SLQ_DEBUG_TRACE
+  a.half_b = getenv("SLQ_HALF_B") != nullptr;
+#endif
   a.a_im2col = c->a_im2col;
   a.chunks_per_tap = geom.Cin / SWZ;
   a.num_kb = geom.kh * geom.kw * a.chunks_per_tap;
