@@ -299,8 +299,9 @@ SLQ_API int slq_stem_forward(const float *x, int32_t N, int32_t H, int32_t W, co
 /* The same stem on the tensor cores (the product path; slq_stem_forward above is the exact-fp32
  * CUDA-core version kept as on-device checker and for W > 256).  Operands pass through tcgen05 as
  * fp16 with fp32 accumulation -- these weights are NOT quantised (the reference keeps them fp32).
- * `workspace` (slq_stem_workspace_bytes, 256-byte aligned, caller-owned) holds the row-expanded
- * fp16 image, the pre-pool u8 activations and the fp16 weight matrix.
+ * `workspace` (slq_stem_workspace_bytes, 256-byte aligned, caller-owned) holds the weight matrix in the
+ * kernel's K order (fp16 and fp32: the BN scale is folded in before the rounding to fp16); activations
+ * never leave the SM.
  * out: u8 NHWC [N,Hp,Wp,64] (SLQ_OUT_U8, scale act_scales[out_id]) or fp32 (SLQ_OUT_F32; then
  * f32_scratch must hold N*Hc*Wc*64 floats).                                                      */
 typedef struct slq_stem slq_stem;

@@ -63,7 +63,7 @@ struct BtArgs {
   uint32_t *out_rowsum;
   long long *stats;  // debug build: wait statistics of CTA 0, or NULL
   int dbg;  // $SLQ_BT_DBG (debug build only, timing experiments): 1 no constant loads, 2 no limb TMEM loads, 4 no staging /
-            // store, 8 no downsample MMAs, 32 no epilogue arithmetic
+            // store, 8 no downsample MMAs, 32 results overwritten (the arithmetic itself still runs: a runtime flag)
 };
 #define BT_DBG(a) (kDebugTrace ? (a).dbg : 0)
 // wait statistics of CTA 0 (debug build, slq_debug_set_trace with a buffer of >= 16 int64): cycles a role spent blocked
