@@ -238,6 +238,26 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c, int bn_ch) {
                       : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
 
+// Two residual bytes (b, b + 1 of word w; b = 0 or 2) as exact floats WITHOUT the conversion unit: a byte
+// permute plants each byte in the mantissa of 2^23 (0x4B0000xx = 8388608 + x), one packed fma(m, 1, -2^23)
+// takes the offset off again (exact: the difference is an integer < 2^24).  `I2F.U8` runs on the quarter-rate
+// XU pipe through the MIO queue -- with one per output it was the top stall reason of the expansion layers'
+// epilogue (profiles/r2_conv_expand_stall_sites.txt): 115.2 us against 119.2 on 64->256 @56^2, 2-5 % on every
+// expansion layer.
+__device__ __forceinline__ float2 res_pair(uint32_t w, int b, bool is_signed) {
+  const uint32_t b0 = (w >> (8 * b)) & 255u, b1 = (w >> (8 * b + 8)) & 255u;
+  // signed residuals (BasicBlock downsample branches) keep the conversion unit: measured 1.4 % faster there
+  if (is_signed) return make_float2((float)(int)(int8_t)b0, (float)(int)(int8_t)b1);
+#ifdef SLQ_RES_I2F  // A/B timing: the conversion-unit form for unsigned bytes too
+  return make_float2((float)b0, (float)b1);
+#else
+  const uint32_t m0 = __byte_perm(w, 0x4B000000u, b == 0 ? 0x7440 : 0x7442);
+  const uint32_t m1 = __byte_perm(w, 0x4B000000u, b == 0 ? 0x7441 : 0x7443);
+  return ffma2(make_float2(__uint_as_float(m0), __uint_as_float(m1)), make_float2(1.0f, 1.0f),
+               make_float2(-8388608.0f, -8388608.0f));
+#endif
+}
+
 // OUT: SLQ_OUT_*;  RES: residual kind
 constexpr int kResNone = 0, kResU8 = 1, kResS8 = 2, kResDyn = 3;  // Dyn: decided at run time (fp32/raw outputs)
 constexpr int kResWide = 4;  // no residual, 256-channel tile: quantised outputs are stored straight from registers
@@ -703,6 +723,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
       mbar_arrive(bready_bar);
     }
+    // debug build, statistics mode: where one epilogue warp (warp 4 of CTA 0) spends a tile -- cycle sums per segment
+    const bool seg_on = kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && warp == 4;
+    long long seg_t = 0, seg_sum[6] = {0, 0, 0, 0, 0, 0};
+    auto seg = [&](int k) {
+      if (seg_on) { const long long t = clock64(); seg_sum[k] += t - seg_t; seg_t = t; }
+    };
+    if (seg_on) seg_t = clock64();
     uint32_t S_next = 0;
     if (!ones_row && team < walk.count) {
       int mt0, nt0;
@@ -742,8 +769,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         walk.at(it + 2, mt2, nt2);
         S_next = window_sum(mt2 * kTileM + row);
       }
+      seg(0);  // loop top: staging / constants barriers, window-sum gather
       mbar_wait_stat(tfull_bar(tb), ph, wepi, kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0);
       tc_fence_after();
+      seg(1);  // accumulator ready
       if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 5, (int)it);
       const int rbuf = has_res ? (int)(it % sp.res_bufs) : 0;
       const uint32_t rsb = smem_base + sp.res_off + rbuf * kOutTileBytes;
@@ -753,6 +782,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         S_raw = tmem_ld1(trow + bn_cols);
         tmem_ld_wait();
       }
+      seg(2);  // residual tile landed, window sum read from TMEM
       const float Sf = (float)S_raw;  // <= 9 * 2048 * 255 < 2^24: exact
       uint32_t rsum = 0;              // channel sum of this thread's u8 outputs of the tile
       if (OUT == SLQ_OUT_ACC && e.out_S && valid && n_tile == 0 && half == 0) e.out_S[m] = (int)S_raw;
@@ -803,10 +833,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                     make_float2(__uint_as_float(pbv[b]), __uint_as_float(pbv[b + 1])));
             float2 y = ffma2(accf, make_float2(__uint_as_float(pav[b]), __uint_as_float(pav[b + 1])), c2);
             if (has_res) {
-              const uint32_t b0 = (rw[q4] >> (8 * b)) & 255u, b1 = (rw[q4] >> (8 * b + 8)) & 255u;
-              const float2 r = res_signed ? make_float2((float)(int)(int8_t)b0, (float)(int)(int8_t)b1)
-                                          : make_float2((float)b0, (float)b1);
-              y = ffma2(r, R2, y);
+              y = ffma2(res_pair(rw[q4], b, res_signed), R2, y);
             }
             v[b] = y.x; v[b + 1] = y.y;
           }
@@ -838,6 +865,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      seg(3);  // the unit loop: TMEM loads, arithmetic, staging stores
       const bool want_rs = OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr;
       if (want_rs && half == 1) rs_scratch[row] = rsum;  // the other half of the tile's channels adds it below
       tc_fence_before();
@@ -866,11 +894,17 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      seg(4);  // hand-offs: accumulator / residual release, proxy fence, team barrier, TMA store issue
       // per-pixel channel sum of this tile's u8 outputs -> side tensor of the output activation.  LAST in the
       // iteration: a fire-and-forget reduction issued before the proxy fence / barrier above would have its
       // round trip to L2 waited for there, once per tile
       if (OUT == SLQ_OUT_U8 && e.out_rowsum != nullptr && half == 0 && valid)
         e.out_rowsum[(long long)n_tile * g.M + m] = rsum + rs_scratch[row];  // plane n_tile: the whole tile's channels
+      seg(5);
+    }
+    if (seg_on && lane == 0) {
+      for (int k = 0; k < 6; ++k) a.trace[56 + k] = seg_sum[k];
+      a.trace[62] = (walk.count + 1 - team) / 2;
     }
     if (!kWide && a.tma_out && et == 0) tma_store_wait_all();
     if (kDebugTrace && a.trace != nullptr && a.trace_cap < 0 && blockIdx.x == 0 && et == 0) { a.trace[6 + team] = wepi; a.trace[12 + team] = clock64() - tstart_clk; }

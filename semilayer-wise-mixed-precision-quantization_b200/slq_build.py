@@ -30,7 +30,9 @@ def _digest():
         if os.path.isfile(p):
             h.update(n.encode())
             h.update(open(p, "rb").read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    # the flags WITHOUT the checkout's own path: the snapshot on a GPU box lives under another root and must not
+    # look stale there (several ranks would then rebuild the same objects at once)
+    h.update(" ".join(f.replace(ROOT, "<root>") for f in NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
@@ -48,8 +50,18 @@ def build(force=False, verbose=False, debug=False):
         return _build_debug(verbose)
     if not force and not needs_build():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    # one builder at a time (the ranks of a torchrun job all call this): the others wait, then find the stamp current
+    import fcntl
+    with open(os.path.join(HERE, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not needs_build():
+            return LIB
+        return _build_locked(verbose)
+
+
+def _build_locked(verbose):
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     objs = []
     procs = []
     for src in SOURCES:
@@ -64,8 +76,9 @@ def build(force=False, verbose=False, debug=False):
         if p.returncode != 0:
             sys.stderr.write(out.decode())
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", LIB + ".tmp"] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    os.replace(LIB + ".tmp", LIB)  # a process that already mapped the old library keeps its inode
     with open(STAMP, "w") as f:
         f.write(_digest())
     return LIB
@@ -99,5 +112,33 @@ def _build_debug(verbose=False):
     return LIB_DBG
 
 
+def build_variant(name, defines, verbose=False):
+    """A/B build of the same sources with extra -D flags -> libslq_b200_<name>.so (developer tools load it with
+    $SLQ_LIB_VARIANT=<name>; never the product path).  `python slq_build.py --variant resi2f SLQ_RES_I2F`"""
+    lib = os.path.join(HERE, "libslq_b200_%s.so" % name)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    bdir = os.path.join(HERE, "build", name)
+    os.makedirs(bdir, exist_ok=True)
+    procs, objs = [], []
+    for src in SOURCES:
+        obj = os.path.join(bdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-D%s" % d for d in defines] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd))
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            sys.stderr.write(out.decode())
+            raise RuntimeError("nvcc failed on %s" % src)
+    subprocess.check_call([nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
+
+
 if __name__ == "__main__":
+    if "--variant" in sys.argv:
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:], verbose=True))
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose=True, debug="--debug" in sys.argv))
