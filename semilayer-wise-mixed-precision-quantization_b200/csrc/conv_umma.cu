@@ -743,7 +743,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t ph = (uint32_t)((it / kTileBars) & 1);
       const uint32_t stg = stg_base + (dbl_stg ? (uint32_t)((it >> 1) & 1) * kOutTileBytes : 0u);
       volatile uint32_t *rs_scratch = rs_base + ((it >> 1) & 1) * 128;
-      if (!dbl_stg || (n_tile != last_n_tile && OUT != SLQ_OUT_ACC)) {
+      if ((!dbl_stg && (kWide || a.tma_out)) || (n_tile != last_n_tile && OUT != SLQ_OUT_ACC)) {
         // staging tile free again? (the previous TMA store of this team has read it)  With two staging tiles per
         // team nothing is waited for here; the barrier is then only needed before the constants are rewritten
         if (!kWide && a.tma_out && et == 0 && !dbl_stg) tma_store_wait_read();
@@ -849,7 +849,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (kQuant) {
-          if constexpr (!kWide) {
+          if (!kWide && a.tma_out) {
             // shared staging tile: the other team's store of the previous tile must have read it
             if (shared_stg && u == u0 && it >= 1) mbar_wait(stfree_bar(team ^ 1), (uint32_t)(((it - 1) >> 1) & 1));
 #pragma unroll
@@ -1067,6 +1067,9 @@ static int launch_one(slq_conv *c, const EpiDev &e, int tma_out, cudaStream_t st
   a.wgp = packed ? c->wgp : nullptr;
   a.wgp_tile = c->wgp_tile; a.wgp_seg = c->wgp_seg; a.wgp_rowoff = c->wgp_rowoff;
   if (wide) tma_out = 0;  // straight from registers (no staging tile: the smem goes to the operand ring)
+  // (measured, tools/gpu_r2_call24.sh: storing the resident-weight layers' outputs from registers as well -- no staging
+  // tile, no team barrier, no TMA store -- costs 159 us against 128 on 64->256 @56^2 and 82 against 70 on 128->512
+  // @28^2: half-filled 32-byte sectors from 32 lanes at a Cout-byte pitch; equal within 5 % on the small layers)
   const int grid = plan_grid(geom, a.sp, sm_count());
   a.trace = g_trace;
   a.trace_cap = g_trace_cap;

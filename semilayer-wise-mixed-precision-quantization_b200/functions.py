@@ -459,7 +459,10 @@ def make_semilayers(arch, net, device, originaloutputs, listminus, listplus, met
                 cand = net
             else:
                 if work is None:
-                    work = factory(num_classes=1000, pretrained='imagenet')
+                    # built ON the device: the constructor's random init (overwritten by the pretrained state dict
+                    # right away) costs 0.5-0.7 s on the host for ResNet-50 -- a third of an 8-GPU sweep
+                    with torch.device(device if torch.device(device).type == "cuda" else "cpu"):
+                        work = factory(num_classes=1000, pretrained='imagenet')
                     if hasattr(work, "slq_share_calibration"):
                         work.slq_share_calibration(net)
                     work.to(device)

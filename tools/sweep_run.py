@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--hw", type=int, default=224)
     ap.add_argument("--layers", type=int, default=0, help="only the first N layers (0 = all)")
     ap.add_argument("--backend", default="nccl")
+    ap.add_argument("--trace-evals", action="store_true", help="rank 0 logs the wall time of every evaluation to stderr")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -81,6 +82,19 @@ def main():
     if args.layers:
         minus = [r for r in minus if r[2] <= args.layers]
         plus = [r for r in plus if r[2] <= args.layers]
+    if args.trace_evals and rank == 0:  # wall time of every evaluation (and of the gaps between them) on rank 0
+        inner = functions._evaluate
+        last = [time.perf_counter()]
+
+        def timed(*a, **k):
+            t_in = time.perf_counter()
+            out = inner(*a, **k)
+            torch.cuda.synchronize()
+            t_out = time.perf_counter()
+            sys.stderr.write("eval %.1f ms (gap before it %.1f ms)\n" % (1e3 * (t_out - t_in), 1e3 * (t_in - last[0])))
+            last[0] = t_out
+            return out
+        functions._evaluate = timed
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     _, _, orig = functions.evaluate_acc_loss_softmax(net2, dev, imagenet.val_loader)
