@@ -253,6 +253,47 @@ def _fused_tail_ok(t):
     return torch.is_tensor(t) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.is_contiguous()
 
 
+def _to_device(net, device):
+    """``net.to(device)`` (reference functions.py:97), skipped when every parameter and buffer already lives there:
+    the no-op walks ~6000 module / tensor objects (16 ms for ResNet-50) -- once per evaluation that was 1.6 s of a
+    96-candidate sweep whose forward passes take 0.1 s."""
+    dev = torch.device(device)
+    if dev.type == "cuda" and dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    for t in net.parameters():
+        if t.device != dev:
+            return net.to(device)
+    for t in net.buffers():
+        if t.device != dev:
+            return net.to(device)
+    return net
+
+
+_RESIDENT = {"key": None, "loader": None, "batches": None}
+
+
+def _resident_batches(data_loader, device):
+    """An IN-MEMORY loader (a list / tuple of (x, y) host tensors, e.g. imagenet.synthetic_loader or a calibration
+    set) is copied to the device once and the copies are reused by the following evaluations, as long as the
+    loader object and its tensors are unchanged (pointer + version counter per tensor).  Every candidate of a
+    sweep evaluates the same batches: the pageable 38.5 MB per 64 images were copied again for each of them.
+    Streaming loaders (anything else) are passed through."""
+    dev = torch.device(device)
+    if dev.type != "cuda" or not isinstance(data_loader, (list, tuple)):
+        return data_loader
+    try:
+        sig = tuple((x.data_ptr(), x._version, tuple(x.shape), y.data_ptr(), y._version) for x, y in data_loader)
+    except Exception:
+        return data_loader
+    if any(x.is_cuda for x, _y in data_loader):
+        return data_loader
+    key = (id(data_loader), str(dev), sig)
+    if _RESIDENT["key"] != key:
+        _RESIDENT["batches"] = [(x.to(device), y.to(device)) for x, y in data_loader]
+        _RESIDENT["key"], _RESIDENT["loader"] = key, data_loader  # the reference keeps id() from being recycled
+    return _RESIDENT["batches"]
+
+
 def _evaluate(net, device, data_loader, ref_outputs=None, want_probs=True):
     """One pass over the loader: -> (acc, loss, [softmax per batch], KL(ref_outputs || outputs) or None).
 
@@ -261,10 +302,11 @@ def _evaluate(net, device, data_loader, ref_outputs=None, want_probs=True):
     kernel pass (slq_eval_tail) that accumulates into four doubles on the device; they are read back ONCE
     at the end (the reference synchronises three times per evaluation, functions.py:129, and KLdiv loops
     over every sample in Python, functions.py:142-146).  CPU tensors take the stock-torch route."""
-    net.to(device)
+    _to_device(net, device)
     net.eval()
     lib = None
     accum = None
+    data_loader = _resident_batches(data_loader, device)
     labels, preds, outputs = [], [], []
     loss_sum, count, n_img = 0, 0, 0
     kl_sum, kl_n = None, 0
