@@ -83,6 +83,32 @@ def test_fused_eval_tail_matches_reference_sequence():
     assert (np.isnan(r) and np.isnan(f)) or (np.isinf(r) and np.isinf(f)) or abs(r - f) <= 1e-4 * abs(r)
 
 
+def test_resident_loader_cache_follows_the_host_tensors():
+    """An in-memory loader is copied to the device once and reused by later evaluations (functions._resident_batches):
+    the copies must follow in-place changes of the host tensors, a streaming loader must pass through untouched, and a
+    module that already lives on the device must not be walked by net.to() again (same object, same parameters)."""
+    import functions
+    g = torch.Generator().manual_seed(11)
+    loader = [(2 * torch.randn(16, 1000, generator=g), torch.randint(0, 1000, (16,), generator=g)) for _ in range(2)]
+    net = _Passthrough()
+    _, loss0, outs0 = functions.evaluate_acc_loss_softmax(net, "cuda", loader)
+    first = functions._RESIDENT["batches"]
+    _, loss1, _ = functions.evaluate_acc_loss_softmax(net, "cuda", loader)
+    assert functions._RESIDENT["batches"] is first and loss1 == loss0  # reused, same result
+    loader[0][0].mul_(0.5)  # in-place change of a host batch: the version counter moves, the copy is refreshed
+    _, loss2, _ = functions.evaluate_acc_loss_softmax(net, "cuda", loader)
+    _, loss2_r, _ = _reference_eval(loader)
+    assert functions._RESIDENT["batches"] is not first
+    assert loss2 != loss0 and abs(loss2 - loss2_r) <= 2e-6 * abs(loss2_r)
+    gen = ((x, y) for x, y in loader)  # a streaming loader (anything that is not a list / tuple) is not cached
+    assert functions._resident_batches(gen, "cuda") is gen
+    lin = torch.nn.Linear(8, 8).cuda()
+    w_ptr = lin.weight.data_ptr()
+    assert functions._to_device(lin, "cuda") is lin and lin.weight.data_ptr() == w_ptr
+    cpu_lin = torch.nn.Linear(8, 8)
+    assert functions._to_device(cpu_lin, "cuda").weight.is_cuda
+
+
 def test_whole_model_quantizer_one_launch_equals_per_layer_calls():
     import functions
     import resnet
