@@ -14,13 +14,16 @@ timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-agree -
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-agree --no-fuse-tail > gpurun_out/bench_nofuse.log 2> gpurun_out/bench_nofuse.err; echo "nofuse rc=$?"
 python - <<'PY'
 import json
-for f in ("bench", "bench_ref", "bench_nopacked", "bench_nofuse"):
+for f in ("bench", "bench_ref", "bench_nopacked", "bench_nofuse"):  # (the side configurations are printed by hand)
     try:
         d = json.loads([l for l in open("gpurun_out/%s.log" % f) if l.startswith("{")][-1])
         print(f, d["value"], d.get("ms_per_step"), d.get("e2e", {}).get("value"), (d.get("roofline") or {}).get("frac"), (d.get("cpu_baseline") or {}).get("value"))
     except Exception as ex:
         print(f, "failed", ex)
 PY
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -n 2 gpurun_out/smoke.log | cut -c1-200
+timeout 300 python bench.py --arch resnet34 --batch 128 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r34.log 2> gpurun_out/bench_r34.err; echo "r34 rc=$?"
+timeout 300 python bench.py --arch resnet18 --batch 32 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_r18.log 2> gpurun_out/bench_r18.err; echo "r18 rc=$?"
 CMD="python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-agree"
 timeout 600 $CMD > gpurun_out/plain.log 2> gpurun_out/plain.err
 rc=$?; echo "plain rc=$rc"
