@@ -22,9 +22,9 @@ def _free_port():
     return p
 
 
-def _run(world):
+def _run(world, extra=()):
     script = os.path.join(ROOT, "tools", "sweep_run.py")
-    common = ["--arch", "resnet18", "--batches", "1", "--batch", "4", "--layers", "3", "--backend", "gloo"]
+    common = ["--arch", "resnet18", "--batches", "1", "--batch", "4", "--layers", "3", "--backend", "gloo"] + list(extra)
     if world == 1:
         cmd = [sys.executable, script] + common
     else:
@@ -42,3 +42,14 @@ def test_sweep_two_ranks_equal_one_rank():
     assert one["values_sha256"] == two["values_sha256"]  # identical floats after the all_gather
     assert one["ranked_first8"] == two["ranked_first8"]
     assert one["flat_rows"] == two["flat_rows"]
+
+
+def test_sweep_on_the_callers_net_equals_the_work_model_path():
+    """functions.make_semilayers runs candidates 1.. on the caller's net when that net IS the pretrained model
+    (no second model / engine); the general path builds a fresh pretrained work model (reference
+    functions.py:258/393/528).  Same candidate values, and the caller's net leaves with the same weights
+    (candidate 0's layer quantised, quirk Q3)."""
+    fast, general = _run(1), _run(1, ["--force-work-model"])
+    assert fast["values_sha256"] == general["values_sha256"]
+    assert fast["net_after_sha256"] == general["net_after_sha256"]
+    assert fast["ranked_first8"] == general["ranked_first8"]

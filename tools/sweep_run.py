@@ -54,6 +54,9 @@ def main():
     ap.add_argument("--layers", type=int, default=0, help="only the first N layers (0 = all)")
     ap.add_argument("--backend", default="nccl")
     ap.add_argument("--trace-evals", action="store_true", help="rank 0 logs the wall time of every evaluation to stderr")
+    ap.add_argument("--force-work-model", action="store_true",
+                    help="candidates 1.. on a second, freshly built pretrained model even when the caller's net is the "
+                         "pretrained one (the general path; tests compare it with the shortcut)")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -82,6 +85,8 @@ def main():
     if args.layers:
         minus = [r for r in minus if r[2] <= args.layers]
         plus = [r for r in plus if r[2] <= args.layers]
+    if args.force_work_model:
+        functions._is_pretrained = lambda *a, **k: False
     if args.trace_evals and rank == 0:  # wall time of every evaluation (and of the gaps between them) on rank 0
         inner = functions._evaluate
         last = [time.perf_counter()]
@@ -95,6 +100,8 @@ def main():
             last[0] = t_out
             return out
         functions._evaluate = timed
+    if world > 1:  # communicator set-up (lazy, on the first collective) is not part of the sweep
+        dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     _, _, orig = functions.evaluate_acc_loss_softmax(net2, dev, imagenet.val_loader)
@@ -109,6 +116,11 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     vals = np.array([o[1] for o in orders], np.float64)
+    # what the sweep left in the caller's net (quirk Q3: candidate 0's layer quantised, everything else untouched)
+    h = hashlib.sha256()
+    for k, v in sorted(net2.state_dict().items()):
+        if k.endswith("weight") and v.dim() == 4:
+            h.update(v.detach().cpu().numpy().tobytes())
     if rank == 0:
         ranked = [int(i) for i in np.argsort(vals, kind="stable")]
         print(json.dumps({
@@ -116,7 +128,8 @@ def main():
                 args.arch, len(semilayers), args.batches, args.batch, args.hw, args.hw),
             "metric": metric, "world": world, "backend": args.backend if world > 1 else "none",
             "seconds": dt, "candidates_per_s": len(semilayers) / dt,
-            "values_sha256": hashlib.sha256(vals.tobytes()).hexdigest(), "ranked_first8": ranked[:8],
+            "values_sha256": hashlib.sha256(vals.tobytes()).hexdigest(), "net_after_sha256": h.hexdigest(),
+            "ranked_first8": ranked[:8],
             "flat_rows": len(flat), "values_first4": [float(v) for v in vals[:4]]}))
     if world > 1:
         dist.destroy_process_group()
