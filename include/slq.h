@@ -332,7 +332,8 @@ SLQ_API int slq_stem_launch_in(slq_stem *s, const void *x, int32_t in_kind, cons
  * (lo*hi + hi*lo + hi*hi): fp32-class accuracy for weights the reference keeps in fp32.
  *   slq_tail_split_weights: fc_w fp32 [O, C] -> fc_w_split fp32 [2][O][C] ({hi, lo} planes), once per weight change
  *   workspace: slq_tail_workspace_bytes(N, C, O) bytes, 16-byte aligned, caller-owned (pooled {hi, lo} +
- *   the per-split partial sums, which are added in a fixed order: the result is deterministic).          */
+ *   the per-split partial sums, which are added in a fixed order: the result is deterministic).
+ *   C: a multiple of 32, at most 12288 (the pool keeps C integer sums in shared memory).               */
 SLQ_API int64_t slq_tail_workspace_bytes(int32_t N, int32_t C, int32_t O);
 SLQ_API int slq_tail_split_weights(const float *fc_w, int32_t O, int32_t C, float *fc_w_split, void *stream);
 SLQ_API int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t C, const float *act_scales,

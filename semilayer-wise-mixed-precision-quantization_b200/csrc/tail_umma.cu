@@ -291,7 +291,8 @@ extern "C" int slq_tail_forward(const uint8_t *x, int32_t N, int32_t HW, int32_t
                                 float *logits, void *stream) {
   const float *fc_w = fc_w_split;
   SLQ_CHECK_ARG(x && act_scales && fc_w && fc_b && workspace && logits, "slq_tail_forward: null pointer argument");
-  SLQ_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C % 32 == 0 && O > 0, "slq_tail_forward: bad shape (C must be a multiple of 32)");
+  SLQ_CHECK_ARG(N > 0 && HW > 0 && C > 0 && C % 32 == 0 && C <= 12288 && O > 0,
+                "slq_tail_forward: bad shape (C must be a multiple of 32, at most 12288: the pool keeps C sums in shared memory)");
   SLQ_CHECK_ARG(reinterpret_cast<uintptr_t>(x) % 16 == 0 && reinterpret_cast<uintptr_t>(fc_w) % 16 == 0 &&
                     reinterpret_cast<uintptr_t>(workspace) % 16 == 0,
                 "slq_tail_forward: x, fc_w and workspace must be 16-byte aligned");
