@@ -238,24 +238,20 @@ __device__ __forceinline__ uint32_t stage_off(int r, int c, int bn_ch) {
                       : (uint32_t)(r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
 }
 
-// Two residual bytes (b, b + 1 of word w; b = 0 or 2) as exact floats WITHOUT the conversion unit: a byte
-// permute plants each byte in the mantissa of 2^23 (0x4B0000xx = 8388608 + x), one packed fma(m, 1, -2^23)
-// takes the offset off again (exact: the difference is an integer < 2^24).  `I2F.U8` runs on the quarter-rate
-// XU pipe through the MIO queue -- with one per output it was the top stall reason of the expansion layers'
-// epilogue (profiles/r2_conv_expand_stall_sites.txt): 115.2 us against 119.2 on 64->256 @56^2, 2-5 % on every
-// expansion layer.
+// Two residual bytes (b, b + 1 of word w; b = 0 or 2) as exact floats.  `I2F.U8` runs on the quarter-rate XU pipe
+// through the MIO queue -- with one per output it was the busiest pipe of the expansion layers' epilogue (48 % under
+// ncu, profiles/r2_conv_expand_stall_sites.txt) -- so the LOW pair of every word goes another way: a byte permute
+// plants each byte in the mantissa of 2^23 (0x4B0000xx = 8388608 + x) and one packed fma(m, 1, -2^23) takes the
+// offset off again (exact: the difference is an integer < 2^24).  Measured on 64->256 @56^2: all four bytes through
+// I2F.U8 119.2 us, all four through PRMT 115.2, two and two (this) another 2 % better (tools/gpu_r2_call32.sh).
 __device__ __forceinline__ float2 res_pair(uint32_t w, int b, bool is_signed) {
   const uint32_t b0 = (w >> (8 * b)) & 255u, b1 = (w >> (8 * b + 8)) & 255u;
   // signed residuals (BasicBlock downsample branches) keep the conversion unit: measured 1.4 % faster there
   if (is_signed) return make_float2((float)(int)(int8_t)b0, (float)(int)(int8_t)b1);
-#ifdef SLQ_RES_I2F  // A/B timing: the conversion-unit form for unsigned bytes too
-  return make_float2((float)b0, (float)b1);
-#else
-  const uint32_t m0 = __byte_perm(w, 0x4B000000u, b == 0 ? 0x7440 : 0x7442);
-  const uint32_t m1 = __byte_perm(w, 0x4B000000u, b == 0 ? 0x7441 : 0x7443);
+  if (b == 2) return make_float2((float)b0, (float)b1);
+  const uint32_t m0 = __byte_perm(w, 0x4B000000u, 0x7440), m1 = __byte_perm(w, 0x4B000000u, 0x7441);
   return ffma2(make_float2(__uint_as_float(m0), __uint_as_float(m1)), make_float2(1.0f, 1.0f),
                make_float2(-8388608.0f, -8388608.0f));
-#endif
 }
 
 // OUT: SLQ_OUT_*;  RES: residual kind
