@@ -45,7 +45,14 @@ namespace slq {
 
 constexpr int kThreads = 640;   // 20 warps: 96 registers per thread (the epilogue needs them)
 constexpr int kTeam = 256;  // threads of one epilogue team
-constexpr int kOutTileBytes = kTileM * 128;  // u8 output / residual staging tile (128 rows x <=128 B)
+// u8 output / residual staging tile: 128 rows x bn_ch bytes -- 16 KB for 128-channel tiles, 8 KB for 64-channel tiles
+// (the 8 KB that a fixed 16 KB stride wasted per tile are what the 3x3 Cin = 64 layers' ring needs to stay 6 deep)
+inline int out_tile_bytes(const ConvGeom &g) {
+#ifdef SLQ_OUT_TILE_16K  // A/B build: the fixed stride of before
+  return kTileM * 128;
+#endif
+  return kTileM * (g.bn_ch < 128 ? g.bn_ch : 128);
+}
 
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 232448;  // 227 KB: the most dynamic shared memory one CTA may own
@@ -70,6 +77,7 @@ struct SmemPlan {
   int out_bufs;      // output staging tiles: TWO per epilogue team (resident weights, when they fit: the TMA store of a
                      // tile is still reading one while the team fills the other -- one team barrier per tile), one
                      // per team, ONE shared by both (streamed weights), or NONE (256-channel tiles store from registers)
+  int out_tile;      // bytes of one output / residual staging tile (out_tile_bytes)
   int out_off, res_off, prm_off, bar_off;
   int total;         // dynamic smem bytes to request (including 1024 B of alignment slack)
 };
@@ -81,6 +89,7 @@ constexpr int kMaxGroup = 4;
 inline SmemPlan make_plan(const ConvGeom &g, int swz, bool has_res) {
   SmemPlan p{};
   p.a_bytes = kTileM * swz;
+  const int kOutTileBytes = p.out_tile = out_tile_bytes(g);
   p.b_tile_bytes = (g.bn_cols + (g.bn_cols < 256 ? 16 : 0)) * swz;
   const int num_kb = g.Ktot / swz;
   const long long b_all = (long long)num_kb * p.b_tile_bytes;
@@ -429,7 +438,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(rempty_bar(res_buf), res_ph ^ 1);
         if (elect_one()) {
           mbar_expect_tx(rfull_bar(res_buf), res_bytes);
-          tma_load_2d(smem_base + sp.res_off + res_buf * kOutTileBytes, &tmR, rfull_bar(res_buf), nt * g.bn_ch,
+          tma_load_2d(smem_base + sp.res_off + res_buf * sp.out_tile, &tmR, rfull_bar(res_buf), nt * g.bn_ch,
                       mt * kTileM);
         }
         __syncwarp();
@@ -601,7 +610,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t prm_s = smem_base + sp.prm_off + team * 3072;
     const bool shared_stg = sp.out_bufs == 1;  // both teams stage through one tile (stfree hand-off below)
     const bool dbl_stg = sp.out_bufs == 4;     // two tiles per team, alternating: no wait for the store at the loop top
-    const uint32_t stg_base = smem_base + sp.out_off + (shared_stg ? 0 : team * (dbl_stg ? 2 : 1)) * kOutTileBytes;
+    const uint32_t stg_base = smem_base + sp.out_off + (shared_stg ? 0 : team * (dbl_stg ? 2 : 1)) * sp.out_tile;
     float s_in = 1.f, s_res = 0.f, inv_out = 1.f;
     if (OUT != SLQ_OUT_ACC) {
       s_in = e.act_scales[e.in_id];
@@ -737,7 +746,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       walk.at(it, m_tile, n_tile);
       const int acc = it % a.acc_bufs, tb = it % kTileBars;
       const uint32_t ph = (uint32_t)((it / kTileBars) & 1);
-      const uint32_t stg = stg_base + (dbl_stg ? (uint32_t)((it >> 1) & 1) * kOutTileBytes : 0u);
+      const uint32_t stg = stg_base + (dbl_stg ? (uint32_t)((it >> 1) & 1) * sp.out_tile : 0u);
       volatile uint32_t *rs_scratch = rs_base + ((it >> 1) & 1) * 128;
       if ((!dbl_stg && (kWide || a.tma_out)) || (n_tile != last_n_tile && OUT != SLQ_OUT_ACC)) {
         // staging tile free again? (the previous TMA store of this team has read it)  With two staging tiles per
@@ -771,7 +780,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       seg(1);  // accumulator ready
       if (kDebugTrace && a.trace != nullptr && et == 0) trace_ev(a, 17 + team, tn, 5, (int)it);
       const int rbuf = has_res ? (int)(it % sp.res_bufs) : 0;
-      const uint32_t rsb = smem_base + sp.res_off + rbuf * kOutTileBytes;
+      const uint32_t rsb = smem_base + sp.res_off + rbuf * sp.out_tile;
       if (has_res) mbar_wait(rfull_bar(rbuf), (uint32_t)((it / sp.res_bufs) & 1));
       const uint32_t trow = tmem_base + ((uint32_t)(wq * 32) << 16) + acc * a.acc_stride;
       if (ones_row) {
