@@ -790,6 +790,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       seg(2);  // residual tile landed, window sum read from TMEM
       const float Sf = (float)S_raw;  // <= 9 * 2048 * 255 < 2^24: exact
       uint32_t rsum = 0;              // channel sum of this thread's u8 outputs of the tile
+      const bool want_rs_any = e.out_rowsum != nullptr;
       if (OUT == SLQ_OUT_ACC && e.out_S && valid && n_tile == 0 && half == 0) e.out_S[m] = (int)S_raw;
       for (int u = u0; u < u1; ++u) {
         uint32_t lo[CW], hi[CW];
@@ -850,8 +851,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (store_ok) of[q4] = make_float4(v[0], v[1], v[2], v[3]);
           } else {
             pk[q4] = epi_pack4<OUT == SLQ_OUT_S8>(v[0], v[1], v[2], v[3]);
-            if (OUT == SLQ_OUT_U8) rsum = __dp4a(pk[q4], 0x01010101u, rsum);
+            // (the channel sums of the outputs, below, only where a consumer gathers them)
           }
+        }
+        if (OUT == SLQ_OUT_U8 && want_rs_any) {  // one uniform branch around the unit's dot products: layers whose
+#pragma unroll                                  // outputs nobody gathers (every expansion of stages 1-2) skip them
+          for (int q4 = 0; q4 < CW / 4; ++q4) rsum = __dp4a(pk[q4], 0x01010101u, rsum);
         }
         if (kQuant) {
           if (!kWide && a.tma_out) {

@@ -33,7 +33,9 @@ rs_out = torch.zeros((max(cout // 64, 1), case.M), dtype=torch.int32, device=dev
 out_mode = L.OUT_S8 if mode == "w16" else L.OUT_U8
 e = L.Epilogue(ws.data_ptr(), zz.data_ptr(), bb.data_ptr(), sc.data_ptr(), 0, 1, 2 if res is not None else -1, L.ptr(res),
                1 if mode == "sres" else 0, out.data_ptr(), None, out_mode, 0 if mode == "w16" else 1,
-               case.rowsum.data_ptr(), rs_out.data_ptr() if out_mode == L.OUT_U8 else None, 1, case.rowsum.numel())
+               case.rowsum.data_ptr(),
+               rs_out.data_ptr() if out_mode == L.OUT_U8 and not os.environ.get("LT_NO_RS") else None,  # $LT_NO_RS: no consumer gathers the output's channel sums
+               1, case.rowsum.numel())
 best = 1e9
 for rep in range(8):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
