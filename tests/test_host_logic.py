@@ -33,14 +33,18 @@ def test_split_matches_reference(sw, capsys):
     assert min(r[5] for r in minus) == -15 and max(r[5] for r in plus) == 16
 
 
-def test_sweep_and_ranked_list_match_reference(sw, monkeypatch):
+@pytest.mark.parametrize("force_work_model", [False, True])
+def test_sweep_and_ranked_list_match_reference(sw, monkeypatch, force_work_model):
     """functions.make_semilayers_resnet18 + make_quantizedlists on the tiny synthetic loader the
     golden run used (2 batches of 4 images, 64x64): same semilayers, same sensitivities (KL/param),
-    same ranked channel list; candidate 0 mutates the caller's net (reference quirk Q3)."""
+    same ranked channel list; candidate 0 mutates the caller's net (reference quirk Q3).  Both routes of the
+    candidates 1..: on the caller's net (it IS the pretrained model here) and on a fresh work model."""
     import functions
     import imagenet
     import resnet
     cpu_standins.install(monkeypatch)
+    if force_work_model:
+        monkeypatch.setattr(functions, "_is_pretrained", lambda *a, **k: False)
     loader = imagenet.synthetic_loader(2, 4, 64, seed=1)
     monkeypatch.setattr(imagenet, "val_loader", loader)
     torch.manual_seed(0)
